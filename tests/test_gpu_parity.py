@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path (through the C ABI via dgdm_b200's host mirror) against the golden
+fixtures produced by the real reference and against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): per-step denoiser output and guidance gradient rel-err
+(||a-b||_2/||b||_2 over the whole per-step tensor) <= 1e-3 in fp32 modes, <= 2e-2 in bf16; final predicted
+scores within 1e-3; best-design indices exact.  The K4 update and K6 selection are bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dgdm_oracle as orc
+from dgdm_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32_simt": 2e-5, "fp32": 1e-3, "bf16": 2e-2}
+TC_MODES = ["fp32", "bf16"]
+ALL_MODES = ["fp32_simt"] + TC_MODES
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    a, b = a.astype(np.float64).reshape(-1), b.astype(np.float64).reshape(-1)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def g2(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "golden_2d.npz")))
+
+
+@pytest.fixture(scope="module")
+def g3(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "golden_3d.npz")))
+
+
+def make2d(precision, objects, grid, npos):
+    from dgdm_b200.diffusion import Diffusion
+    from dgdm_b200.scheduler import DDIMScheduler
+    return Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(15), 5, mode="point", num_points=14,
+                     classifier_model=syn.dynamics2d_state_dict(0), grid_size=grid, num_pos=npos,
+                     object_vertices=objects, object_ids=list(range(len(objects))), precision=precision)
+
+
+def make3d(precision, objects, starts, grid, npos):
+    from dgdm_b200.diffusion import Diffusion
+    from dgdm_b200.scheduler import DDIMScheduler
+    return Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(15), 5, mode="point_3d", num_points=42,
+                     classifier_model=syn.dynamics3d_state_dict(0), grid_size=grid, num_pos=npos,
+                     object_vertices=objects, object_ids=list(range(len(objects))), fps_starts=starts,
+                     precision=precision)
+
+
+# ---------------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("n", [14 * 4, 14 * 256 * 64, 7, 1001])
+def test_ddim_update_bit_exact(n):
+    from dgdm_b200.scheduler import DDIMScheduler
+    s = DDIMScheduler(15); s.set_timesteps(5)
+    rs = np.random.RandomState(n)
+    x = torch.from_numpy(rs.randn(n).astype(np.float32) * 1.5)
+    e = torch.from_numpy(rs.randn(n).astype(np.float32))
+    g = torch.from_numpy(rs.randn(n).astype(np.float32) * 30)
+    a = orc.ddim_alphas_cumprod(15)
+    for t in (12, 6, 0):
+        for scale, grad in ((0.001, g), (0.5, g), (0.0, None)):
+            eh = e if grad is None else e - (1 - a[t]).sqrt() * grad * scale
+            want = orc.ddim_step(eh, t, x, a, 15, 5)
+            got = s.guided_step(e.cuda(), t, x.cuda(), None if grad is None else grad.cuda(), scale)
+            assert torch.equal(got.cpu(), want), f"t={t} scale={scale}: max diff {(got.cpu() - want).abs().max()}"
+    # diffusers-style API and in-place operation
+    xs = x.cuda()
+    out = s.step(e.cuda(), 3, xs).prev_sample
+    assert torch.equal(out.cpu(), orc.ddim_step(e, 3, x, a, 15, 5))
+    s.guided_step(e.cuda(), 3, xs, None, 0.0, out=xs)
+    assert torch.equal(xs, out)
+
+
+def test_ddim_empty_and_errors():
+    from dgdm_b200 import _lib
+    l = _lib.lib()
+    z = torch.zeros(4, device="cuda")
+    assert l.dgdm_ddim_guided_update(z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 0, 0.1, 0.9, 0.9, 0.1, 1.0, 1, None) == 0
+    assert l.dgdm_ddim_guided_update(z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 4, 0.1, 0.0, 0.9, 0.1, 1.0, 1, None) == -1
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(1, 256, 128), (37, 3, 256), (300, 256, 27), (1000, 64, 3), (129, 130, 131), (16, 28, 256)])
+def test_linear_f32(M, N, K):
+    from dgdm_b200 import _lib
+    rs = np.random.RandomState(M + N + K)
+    A = torch.from_numpy(rs.randn(M, K).astype(np.float32)); W = torch.from_numpy(rs.randn(N, K).astype(np.float32))
+    b = torch.from_numpy(rs.randn(N).astype(np.float32))
+    Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
+    C = torch.empty(M, N, device="cuda")
+    for relu in (0, 1):
+        _lib.check(_lib.lib().dgdm_linear_f32(Ad.data_ptr(), K, Wd.data_ptr(), bd.data_ptr(), C.data_ptr(), N, M, N, K,
+                                              relu, _lib.stream_ptr()))
+        want = torch.nn.functional.linear(A.double(), W.double(), b.double())
+        want = torch.relu(want) if relu else want
+        assert rel(C, want) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- K3
+def test_unet_golden(g2, g3):
+    dm = make2d("fp32_simt", torch.from_numpy(g2["objects"]), int(g2["grid_size"]), int(g2["num_pos"]))
+    for g in (g2, g3):
+        x = torch.from_numpy(g["noise"])
+        for t in (12, 0):
+            got = dm.noise_pred_net(x.cuda(), torch.full((x.shape[0],), t, dtype=torch.int64))
+            assert got.shape == x.shape
+            assert rel(got, g[f"unet_t{t}"]) < 1e-4, (t, rel(got, g[f"unet_t{t}"]))
+
+
+@pytest.mark.parametrize("n,P", [(1, 14), (300, 14), (4100, 14), (130, 42)])
+def test_unet_vs_oracle(n, P, g2):
+    dm = make2d("fp32_simt", torch.from_numpy(g2["objects"]), 2, 1)
+    x = syn.initial_noise(n, P, seed=5)
+    with torch.no_grad():
+        want = orc.unet1d_forward(syn.unet1d_state_dict(0), x, torch.full((n,), 9, dtype=torch.int64))
+    got = dm.noise_pred_net(x.cuda(), 9)
+    assert rel(got, want) < 1e-4
+    # worst single sample, too
+    per = (got.cpu() - want).reshape(n, -1).norm(dim=1) / want.reshape(n, -1).norm(dim=1)
+    assert float(per.max()) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- K1+K2
+@pytest.mark.parametrize("precision", ALL_MODES)
+def test_cond_fn_2d_golden(g2, precision):
+    objs = torch.from_numpy(g2["objects"])
+    dm = make2d(precision, objs, int(g2["grid_size"]), int(g2["num_pos"]))
+    x = torch.from_numpy(g2["noise"]).cuda()
+    for oi in range(2):
+        for t in (12, 3):
+            for name in ("rotate", "rotate_clockwise", "clockwise_up", "shift_left", "counterclockwise_right"):
+                got = dm.cond_fn(x, torch.full((4,), t, dtype=torch.int64), opt_obj=name, object_vertices=dm.object_vertices[oi])
+                r = rel(got, g2[f"grad_o{oi}_t{t}_{name}"])
+                assert got.shape == (4, 14, 1) and r < TOL[precision], (oi, t, name, r)
+        got = dm.cond_fn(x, 6, opt_obj="rotate", object_vertices=dm.object_vertices[oi], ori_range=[-0.5, 0.25])
+        assert rel(got, g2[f"grad_o{oi}_t6_rotate_narrow"]) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ALL_MODES)
+def test_guided_loop_2d_golden(g2, precision):
+    dm = make2d(precision, torch.from_numpy(g2["objects"]), int(g2["grid_size"]), int(g2["num_pos"]))
+    noise = torch.from_numpy(g2["noise"])
+    for name in ("rotate_clockwise", "rotate"):
+        trace = []
+        out = dm.guided_sample(0, 4, noise, opt_obj=name, trace=trace)
+        for i, rec in enumerate(trace):
+            for oi in range(2):
+                assert rel(rec["eps"][oi], g2[f"loop_{name}_eps_o{oi}_s{i}"]) < max(1e-4, TOL[precision])
+                assert rel(rec["grad"][oi], g2[f"loop_{name}_grad_o{oi}_s{i}"]) < max(1e-4, TOL[precision])
+                assert rel(rec["sample"][oi], g2[f"loop_{name}_sample_o{oi}_s{i}"]) < max(1e-4, TOL[precision])
+        assert out["designs"].shape == (2, 4, 14, 1) and out["scores"].shape == (2, 4)
+    trace = []
+    dm.guided_sample_multi_object(0, 4, noise, opt_obj="shift_up", trace=trace)
+    for i, rec in enumerate(trace):
+        for k in ("eps", "grad", "sample"):
+            assert rel(rec[k], g2[f"multi_shift_up_{k}_s{i}"]) < max(1e-4, TOL[precision]), (i, k)
+
+
+@pytest.mark.parametrize("precision", ALL_MODES)
+def test_convergence_2d_golden(g2, precision):
+    dm = make2d(precision, torch.from_numpy(g2["objects"]), int(g2["grid_size"]), int(g2["num_pos"]))
+    noise = torch.from_numpy(g2["noise"])
+    ung = dm.unguided_sample(noise)
+    assert rel(ung, g2["unguided"]) < 1e-4
+    ung = torch.from_numpy(g2["unguided"])
+    for oi in range(2):
+        c = dm.get_convergence_centers(ung, dm.object_vertices[oi], 4)
+        assert c.tolist() == g2[f"conv_centers_o{oi}"].tolist()
+        got = dm.cond_fn(noise, 9, opt_obj="convergence", object_vertices=dm.object_vertices[oi], convergence_centers=c)
+        assert rel(got, g2[f"grad_o{oi}_t9_convergence"]) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ALL_MODES)
+def test_profile_scores_and_selection_2d(g2, precision):
+    dm = make2d(precision, torch.from_numpy(g2["objects"]), int(g2["grid_size"]), int(g2["num_pos"]))
+    final = torch.from_numpy(g2["loop_rotate_clockwise_sample_o0_s4"])
+    lg = dm.profile_logits(final, dm.object_vertices[0])                      # (B, grid, 3) pair-major
+    want = g2["profile_logits_o0"].reshape(int(g2["grid_size"]), 4, 3).transpose(1, 0, 2)
+    assert rel(lg, want) < TOL[precision]
+    sc = dm.score(final.reshape(4, -1).cuda(), dm._obj_dev[:1], 1, "rotate_clockwise")
+    assert np.allclose(sc.cpu().numpy(), -want[..., 0].mean(1), atol=1e-3)
+    idx, best = dm.best_of_n(sc[None], 4)
+    assert idx[0].tolist() == orc.top_k(torch.from_numpy(-want[..., 0].mean(1)), 4).tolist()
+
+
+@pytest.mark.parametrize("precision", ALL_MODES)
+@pytest.mark.parametrize("B,grid,npos,n_obj", [(5, 7, 3, 3), (32, 12, 2, 2), (1, 1, 1, 1), (3, 150, 1, 2)])
+def test_cond_fn_2d_vs_oracle_ragged(precision, B, grid, npos, n_obj):
+    """Ragged shapes: G not a multiple of the 128-row tile, pairs straddling tiles, single row."""
+    objs = syn.objects_2d(n_obj, seed_base=1500)
+    dm = make2d(precision, objs, grid, npos)
+    samp = orc.OracleSampler("point", syn.unet1d_state_dict(0), syn.dynamics2d_state_dict(0), objs, grid, npos)
+    x = syn.initial_noise(B, 14, seed=3)
+    for name, t in (("rotate", 9), ("counterclockwise_left", 0)):
+        want = torch.stack([samp.cond_fn(x, t, name, oi) for oi in range(n_obj)])
+        got = dm.guidance(x[..., 0].cuda().repeat(n_obj, 1).contiguous(), t, dm._obj_dev, 1, name).reshape(n_obj, B, 14, 1)
+        assert rel(got, want) < TOL[precision], (name, rel(got, want))
+        # multi-object pairing: every design against every object, averaged
+        gm = dm.guidance(x[..., 0].cuda().contiguous(), t, dm._obj_dev, n_obj, name, grad_mul=1.0 / n_obj)
+        assert rel(gm.reshape(B, 14, 1), want.mean(0)) < TOL[precision]
+
+
+# ---------------------------------------------------------------------------------------------- K5 + 3D
+def test_pointnet2_golden(g3):
+    dm = make3d("fp32_simt", torch.from_numpy(g3["objects"]), torch.from_numpy(g3["fps_starts"]), int(g3["grid_size"]), int(g3["num_pos"]))
+    for oi in range(2):
+        assert rel(dm._obj_dev[oi], g3[f"code_o{oi}"][0]) < 1e-4
+
+
+def test_pointnet2_many_objects_vs_oracle():
+    n = 70                                     # crosses the 64-cloud chunk
+    objs, st = syn.objects_3d(n, seed_base=2500), syn.fps_starts(n, seed_base=3500)
+    dm = make3d("fp32_simt", objs, st, 3, 1)
+    sd = orc.strip_prefix(syn.dynamics3d_state_dict(0))
+    with torch.no_grad():
+        want = orc.pointnet2_encode(sd, objs.permute(0, 2, 1).contiguous(), st)
+    per = (dm._obj_dev.cpu() - want).norm(dim=1) / want.norm(dim=1)
+    assert float(per.max()) < 1e-4, per
+
+
+@pytest.mark.parametrize("precision", ALL_MODES)
+def test_cond_fn_3d_golden(g3, precision):
+    dm = make3d(precision, torch.from_numpy(g3["objects"]), torch.from_numpy(g3["fps_starts"]), int(g3["grid_size"]), int(g3["num_pos"]))
+    x = torch.from_numpy(g3["noise"]).cuda()
+    for oi in range(2):
+        for t, name in ((12, "rotate_clockwise"), (6, "rotate"), (0, "counterclockwise_down")):
+            got = dm.cond_fn(x, t, opt_obj=name, object_vertices=dm.object_vertices[oi])
+            assert rel(got, g3[f"grad_o{oi}_t{t}_{name}"]) < TOL[precision], (oi, t, name)
+
+
+@pytest.mark.parametrize("precision", ALL_MODES)
+def test_guided_loop_3d_golden(g3, precision):
+    dm = make3d(precision, torch.from_numpy(g3["objects"][:1]), torch.from_numpy(g3["fps_starts"][:1]), int(g3["grid_size"]), int(g3["num_pos"]))
+    trace = []
+    dm.guided_sample(0, 3, torch.from_numpy(g3["noise"]), opt_obj="rotate_clockwise", trace=trace)
+    for i, rec in enumerate(trace):
+        for k in ("eps", "grad", "sample"):
+            assert rel(rec[k][0], g3[f"loop_{k}_s{i}"]) < max(2e-4, TOL[precision]), (i, k)
+
+
+# ---------------------------------------------------------------------------------------------- K6
+def test_best_of_n_ties_nan_and_topk():
+    dm = make2d("fp32_simt", syn.objects_2d(1), 2, 1)
+    rs = np.random.RandomState(0)
+    s = rs.randint(0, 6, size=(9, 300)).astype(np.float32)      # many exact ties
+    idx, best = dm.best_of_n(torch.from_numpy(s), 8)
+    assert idx.cpu().tolist() == orc.top_k(torch.from_numpy(s), 8).tolist()
+    assert np.array_equal(best.cpu().numpy(), np.take_along_axis(s, idx.cpu().numpy(), 1))
+    one, _ = dm.best_of_n(torch.from_numpy(s), 1)
+    assert one[:, 0].cpu().tolist() == np.argmax(s, axis=1).tolist()
+    s2 = torch.tensor([[float("nan"), 1.0, 1.0, -3.0]])
+    assert dm.best_of_n(s2, 3)[0].cpu().tolist() == [[1, 2, 3]]
+    with pytest.raises(Exception):
+        dm.best_of_n(torch.zeros(2, 3), 4)
+
+
+# ---------------------------------------------------------------------------------------------- errors
+def test_error_behaviour_matches_reference():
+    from dgdm_b200.diffusion import Diffusion
+    from dgdm_b200.scheduler import DDIMScheduler
+    dm = make2d("fp32_simt", syn.objects_2d(1), 2, 1)
+    x = syn.initial_noise(2, 14)
+    with pytest.raises(ValueError, match="opt obj not supported"):
+        dm.cond_fn(x, 3, opt_obj="spin", object_vertices=dm.object_vertices[0])
+    with pytest.raises(ValueError, match="object vertices not provided"):
+        dm.cond_fn(x, 3, opt_obj="rotate", object_vertices=None)
+    with pytest.raises(ValueError, match="model type not supported"):
+        Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(15), 5, mode="image", classifier_model=syn.dynamics2d_state_dict(0),
+                  object_vertices=syn.objects_2d(1))
+    with pytest.raises(ValueError):
+        dm.guided_sample(0, 3, x)                                 # batch_size / noise mismatch
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("precision", TC_MODES)
+def test_full_size_properties_2d(precision):
+    """At a BASELINE-sized slice (256 candidates x 900 pose rows per object) the oracle is too slow, so check
+    size-independent properties: (1) linearity of the gradient in the objective coefficients, (2) the batched
+    result equals per-object calls, (3) the tensor-core result agrees with the exact-fp32 CUDA-core path."""
+    n_obj, B, grid, npos = 4, 256, 36, 5
+    objs = syn.objects_2d(n_obj)
+    dm = make2d(precision, objs, grid, npos)
+    ref = make2d("fp32_simt", objs, grid, npos)
+    x = syn.initial_noise(B, 14)[..., 0].cuda().repeat(n_obj, 1).contiguous()
+    g_cw = dm.guidance(x, 6, dm._obj_dev, 1, "rotate_clockwise")
+    g_up = dm.guidance(x, 6, dm._obj_dev, 1, "shift_up")
+    g_cu = dm.guidance(x, 6, dm._obj_dev, 1, "clockwise_up")
+    assert rel(g_cu, g_cw + g_up) < (1e-4 if precision == "fp32" else 2e-2)
+    one = dm.guidance(x[B:2 * B].contiguous(), 6, dm._obj_dev[1:2].contiguous(), 1, "clockwise_up")
+    assert torch.equal(one, g_cu[B:2 * B])
+    exact = ref.guidance(x, 6, ref._obj_dev, 1, "clockwise_up")
+    assert rel(g_cu, exact) < TOL[precision]
+    per = (g_cu - exact).norm(dim=1) / exact.norm(dim=1)
+    print(f"[{precision}] aggregate rel-err {rel(g_cu, exact):.3e}, worst candidate {float(per.max()):.3e}")
