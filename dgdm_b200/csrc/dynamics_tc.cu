@@ -1,15 +1,613 @@
-// placeholder until the tcgen05 trunk lands
+// K1 (tensor-core path) + K2: the dynamics-network trunk, forward + input-gradient backward, fused per
+// 128-row tile on tcgen05 / TMEM, with the guidance reduction over pose rows fused on the tail.
+//
+// Work per guidance row r = (pair p, pose g)   [reference: dynamics/profile_forward_2d.py:109-135,154-155 forward,
+// torch.autograd.grad at generator/diffusion.py:503-504 backward]:
+//     a1 = relu(Cst[obj(p)] + U[design(p)] + V[g])                                  (hoisted layer 1)
+//     a_l = relu(a_{l-1} W_l^T + b_l), l = 2..8 ;  logits = a_8 W_out^T + b_out      (7 + 1 GEMMs)
+//     d8 = (dObj/dlogits . W_out) * 1[a_8>0] ;  d_{l-1} = (d_l W_l) * 1[a_{l-1}>0]    (7 GEMMs)
+//     dUp[p] += d_1                                                                 (K2: sum over g)
+// = 2*2*(7*256^2 + 256*3) = 1 838 080 FLOP per row (2D), none of it ever touching HBM: the row's activations
+// live in TMEM, only ReLU sign bits (32 B per layer per row) are kept, in shared memory.
+//
+// Mapping to the SM (one persistent CTA per SM, 10 warps):
+//   warp 8   producer: streams weight tiles global(L2) -> smem ring with cp.async.bulk (TMA unit, UBLKCP),
+//            completion on mbarriers.  Tiles are pre-swizzled (128B swizzle, K-major) by dgdm_dyn_pack_tc so
+//            the bytes land exactly in the canonical UMMA layout.
+//   warp 9   MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16, M=128 (tile rows) x N=256 x K=16,
+//            A operand from TMEM (the activations), B from smem (the weight tile), D (fp32) in TMEM;
+//            tcgen05.commit releases smem stages and signals the epilogue.
+//   warps 0-7 epilogue: tcgen05.ld the accumulator, bias + ReLU (or ReLU-mask in the backward), collect
+//            sign bits, convert to bf16 (hi [+ lo]) and tcgen05.st it back as the next layer's A operand.
+//            The last backward layer is reduced over the tile's rows per pair with warp shuffles and written
+//            to a per-(pair,tile) slot; a small second kernel adds the slots in fixed order (deterministic).
+// TMEM map (512 columns): A_hi [0,128) | A_lo [128,256) | D [256,512).
+//
+// Precision modes: BF16X3 splits both operands into bf16 hi + lo and issues 3 MMAs (hi*hi, lo*hi, hi*lo) into
+// the same fp32 accumulator: ~2^-16 relative product error, fp32-grade (<=1e-3 end to end).  BF16 issues one.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+
 namespace dgdm {
-size_t tc_trunk_workspace_bytes(int, int64_t, int) { return 256; }
-int tc_trunk(const dgdm_dyn_weights*, const float*, const float*, const float*, int, int, int, const int32_t*, int,
-             const dgdm_objective*, bool, float*, float*, float*, void*, size_t, int, cudaStream_t) {
-  set_error("tensor-core trunk not built");
-  return DGDM_EUNSUPPORTED;
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int KBLK = 64;                       // bf16 elements per k-block row = 128 bytes = one swizzle span
+constexpr int WTILE_BYTES = 256 * KBLK * 2;    // 32 KB: 256 rows x 128 B
+constexpr int NSTAGE = 5;
+constexpr int NTHREADS = 320;
+constexpr int MAX_SEG = 20;
+constexpr int MASK_WORDS = 16 + 7 * 8;         // layer 1 up to 512 wide + 7 layers of 256
+constexpr uint32_t TMEM_A_HI = 0, TMEM_A_LO = 128, TMEM_D = 256;
+
+enum { K_FWD = 0, K_MID = 1, K_OUT = 2, K_BWD = 3, K_LAST = 4 };
+
+struct Seg {
+  uint32_t img_off;    // byte offset of the segment's tiles in the image
+  uint16_t n_rows;     // B-operand rows = MMA N (256 or 16)
+  uint8_t kind, layer, half, accum;
+};
+
+struct TcParams {
+  const uint8_t* img;
+  const float* U; const float* Cst; const float* V;
+  const float* bias[7]; const float* w_out; const float* b_out;
+  const int32_t* pair_object;
+  float* part;          // [n_slots][H1] per-(pair,tile) partial column sums  (backward)
+  float* score_part;    // [n_slots] per-(pair,tile) partial objective sums   (forward only)
+  float* logits;        // optional [n_rows,3]
+  int* err;             // device error flag (mbarrier timeout)
+  dgdm_objective obj;
+  int64_t n_rows;       // n_pairs * G
+  int n_tiles, G, H1, opd, n_designs, n_obj, n_seg, x3, backward;
+  Seg seg[MAX_SEG];
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps with an error code instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if (it > (1u << 24)) {
+      if (err) atomicExch(err, code);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T ; kind::f16 (bf16 in, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of one weight tile: K-major, 128-byte swizzle, rows of 128 B,
+// 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__device__ __forceinline__ int pair_obj(int64_t p, int opd, int n_designs, int n_obj, const int32_t* pair_object) {
+  if (pair_object) return pair_object[p];
+  if (opd == 1) return (int)(p / (n_designs / n_obj));
+  return (int)(p % opd);
+}
+
+// Split 32 fp32 values into packed bf16 hi (and lo = rn(v - hi)) pairs; element 2i in the low half.
+__device__ __forceinline__ void split_pack(const float (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    float2 hf = __bfloat1622float2(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    hi[i] = *reinterpret_cast<uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<uint32_t*>(&l);
+  }
+}
+
+// Column sums over the 32 lanes of a warp for 32 per-lane values: after the butterfly lane i holds
+// sum over lanes of v[i].  31 shuffles instead of 32*5.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      float keep = upper ? v[i + w] : v[i];
+      float send = upper ? v[i] : v[i + w];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
+struct Smem {
+  uint64_t full[NSTAGE], empty[NSTAGE], a_ready, d_ready;
+  uint32_t tmem_base, pad_;
+  float bias[7][256];
+  float w_out[3][256];
+  float b_out[4];
+  float red[4][256];            // per lane-quadrant partial column sums
+  float red_s[4];
+  uint32_t mask[MASK_WORDS][TILE_M];
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  // weight ring first (1024-byte aligned for the 128B swizzle), bookkeeping after
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Smem& S = *reinterpret_cast<Smem*>(ring + NSTAGE * WTILE_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.a_ready, 8);
+    mbar_init(&S.d_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 7 * 256; i += NTHREADS) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256];
+  for (int i = tid; i < 3 * 256; i += NTHREADS) S.w_out[i / 256][i % 256] = P.w_out[i];
+  if (tid < 3) S.b_out[tid] = P.b_out[tid];
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+
+  const int tiles_mine = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tiles_per_seg = P.x3 ? 8 : 4;       // weight tiles per segment: 4 k-blocks x (hi [, lo])
+
+  if (warp == 8) {
+    // =============================== producer ===============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < tiles_mine; ++t) {
+        for (int sg = 0; sg < P.n_seg; ++sg) {
+          const Seg sgm = P.seg[sg];
+          const uint32_t tile_bytes = (uint32_t)sgm.n_rows * 128u;
+          for (int j = 0; j < tiles_per_seg; ++j) {
+            // image order inside a segment: kb0.hi, kb0.lo, kb1.hi, kb1.lo, ...
+            const int kb = P.x3 ? (j >> 1) : j, part = P.x3 ? (j & 1) : 0;
+            mbar_wait(&S.empty[stage], phase ^ 1, P.err, 1);
+            mbar_arrive_expect_tx(&S.full[stage], tile_bytes);
+            bulk_g2s(ring + stage * WTILE_BYTES, P.img + sgm.img_off + (size_t)(kb * 2 + part) * tile_bytes, tile_bytes,
+                     &S.full[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      for (int t = 0; t < tiles_mine; ++t) {
+        for (int sg = 0; sg < P.n_seg; ++sg) {
+          const Seg sgm = P.seg[sg];
+          const uint32_t idesc = make_idesc(sgm.n_rows);
+          mbar_wait(&S.a_ready, a_phase, P.err, 2);
+          a_phase ^= 1;
+          tc_fence_after();
+          uint32_t accum = sgm.accum;
+          for (int j = 0; j < tiles_per_seg; ++j) {
+            const int kb = P.x3 ? (j >> 1) : j, part = P.x3 ? (j & 1) : 0;
+            mbar_wait(&S.full[stage], phase, P.err, 3);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(ring + stage * WTILE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < KBLK / 16; ++ks) {
+              const uint64_t bdesc = make_b_desc(b_addr + ks * 32);
+              const uint32_t a_col = (uint32_t)(kb * (KBLK / 2) + ks * 8);     // 16 bf16 = 8 TMEM columns
+              tc_mma_ts(tmem + TMEM_D, tmem + TMEM_A_HI + a_col, bdesc, idesc, accum);
+              accum = 1;
+              if (P.x3 && part == 0) tc_mma_ts(tmem + TMEM_D, tmem + TMEM_A_LO + a_col, bdesc, idesc, 1);
+            }
+            tc_commit(&S.empty[stage]);           // stage reusable once these MMAs have read it
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&S.d_ready);                  // accumulator complete
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue warps 0..7 ===============================
+    const int q = warp & 3, h = warp >> 2;        // TMEM lane quadrant, column half
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const int l1_words = P.H1 / 32;
+    uint32_t d_phase = 0;
+
+    for (int t = 0; t < tiles_mine; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int64_t r_glob = (int64_t)tile * TILE_M + row;
+      const bool live = r_glob < P.n_rows;
+      const int64_t pr = live ? r_glob / P.G : -1;
+      const int g = live ? (int)(r_glob % P.G) : 0;
+      const float coef = (live && P.obj.row_coef) ? P.obj.row_coef[r_glob] : 1.f;
+      const float* u_row = nullptr; const float* c_row = nullptr; const float* v_row = nullptr;
+      if (live) {
+        u_row = P.U + (pr / P.opd) * P.H1;
+        c_row = P.Cst + (int64_t)pair_obj(pr, P.opd, P.n_designs, P.n_obj, P.pair_object) * P.H1;
+        v_row = P.V + (int64_t)g * P.H1;
+      }
+      const int64_t p_first = ((int64_t)tile * TILE_M) / P.G;
+      int64_t last_row = (int64_t)tile * TILE_M + TILE_M - 1;
+      if (last_row >= P.n_rows) last_row = P.n_rows - 1;
+      const int64_t p_last = last_row / P.G;
+
+      // layer-1 activations for K-half `kh` -> A operand + layer-1 sign bits
+      auto build_a1 = [&](int kh) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = kh * 256 + h * 128 + c * 32;
+          float v[32];
+          uint32_t bits = 0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+              float4 k4 = *reinterpret_cast<const float4*>(c_row + col0 + i);
+              float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + i);
+              float4 v4 = *reinterpret_cast<const float4*>(v_row + col0 + i);
+              a.x = (k4.x + u4.x) + v4.x; a.y = (k4.y + u4.y) + v4.y; a.z = (k4.z + u4.z) + v4.z; a.w = (k4.w + u4.w) + v4.w;
+            }
+            v[i] = fmaxf(a.x, 0.f); v[i + 1] = fmaxf(a.y, 0.f); v[i + 2] = fmaxf(a.z, 0.f); v[i + 3] = fmaxf(a.w, 0.f);
+            bits |= (a.x > 0.f ? 1u : 0u) << i | (a.y > 0.f ? 1u : 0u) << (i + 1) | (a.z > 0.f ? 1u : 0u) << (i + 2) |
+                    (a.w > 0.f ? 1u : 0u) << (i + 3);
+          }
+          S.mask[kh * 8 + h * 4 + c][row] = bits;
+          uint32_t hi[16], lo[16];
+          split_pack(v, hi, lo);
+          const uint32_t acol = (uint32_t)(h * 64 + c * 16);
+          tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
+          if (P.x3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+        }
+      };
+      auto signal_a = [&]() {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.a_ready);
+      };
+
+      build_a1(0);
+      signal_a();
+
+      float dl0 = 0.f, dl1 = 0.f, dl2 = 0.f;
+      for (int sg = 0; sg < P.n_seg; ++sg) {
+        const Seg sgm = P.seg[sg];
+        mbar_wait(&S.d_ready, d_phase, P.err, 4);
+        d_phase ^= 1;
+        tc_fence_after();
+        const bool last_seg = sg == P.n_seg - 1;
+
+        if (sgm.kind == K_MID) {
+          build_a1(1);
+        } else if (sgm.kind == K_FWD || sgm.kind == K_BWD) {
+          // FWD: a = relu(D + b), record sign bits of layer `layer`.   BWD: d = D * 1[a_{layer} > 0].
+          const int mbase = sgm.layer == 0 ? 0 : l1_words + (sgm.layer - 1) * 8;   // mask row of trunk layer index
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t rr[32];
+            tmem_ld32(lane_addr + TMEM_D + (uint32_t)(h * 128 + c * 32), rr);
+            float v[32];
+            if (sgm.kind == K_FWD) {
+              const float* b = &S.bias[sgm.layer - 1][h * 128 + c * 32];
+              uint32_t bits = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float z = __uint_as_float(rr[i]) + b[i];
+                bits |= (z > 0.f ? 1u : 0u) << i;
+                v[i] = fmaxf(z, 0.f);
+              }
+              S.mask[mbase + h * 4 + c][row] = bits;
+            } else {
+              const uint32_t bits = S.mask[mbase + h * 4 + c][row];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? __uint_as_float(rr[i]) : 0.f;
+            }
+            uint32_t hi[16], lo[16];
+            split_pack(v, hi, lo);
+            const uint32_t acol = (uint32_t)(h * 64 + c * 16);
+            tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
+            if (P.x3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+          }
+        } else if (sgm.kind == K_OUT) {
+          uint32_t rr[8];
+          tmem_ld8(lane_addr + TMEM_D, rr);
+          const float l0 = __uint_as_float(rr[0]) + S.b_out[0], l1 = __uint_as_float(rr[1]) + S.b_out[1],
+                      l2 = __uint_as_float(rr[2]) + S.b_out[2];
+          if (h == 0 && live && P.logits) {
+            float* o = P.logits + r_glob * 3;
+            o[0] = l0; o[1] = l1; o[2] = l2;
+          }
+          if (!P.backward) {
+            // forward only: per-pair sums of the objective over this tile's rows -> score_part[p + tile]
+            const float val = live ? coef * (P.obj.c[0] * l0 + P.obj.c[1] * l1 + P.obj.c[2] * l2 + P.obj.sq0 * l0 * l0) : 0.f;
+            for (int64_t ps = p_first; ps <= p_last; ++ps) {
+              float s = (pr == ps) ? val : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+              if (h == 0 && lane == 0) S.red_s[q] = s;
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (tid == 0) P.score_part[ps + tile] = (S.red_s[0] + S.red_s[1]) + (S.red_s[2] + S.red_s[3]);
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+          } else {
+            // seed of the backward pass: d8 = (dObj/dlogits . W_out) * 1[a_8 > 0]
+            dl0 = coef * (P.obj.c[0] + 2.f * P.obj.sq0 * l0); dl1 = coef * P.obj.c[1]; dl2 = coef * P.obj.c[2];
+            const int mbase = l1_words + 6 * 8;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              const int col0 = h * 128 + c * 32;
+              const uint32_t bits = S.mask[mbase + h * 4 + c][row];
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float d = dl0 * S.w_out[0][col0 + i] + dl1 * S.w_out[1][col0 + i] + dl2 * S.w_out[2][col0 + i];
+                v[i] = (bits >> i) & 1u ? d : 0.f;
+              }
+              uint32_t hi[16], lo[16];
+              split_pack(v, hi, lo);
+              const uint32_t acol = (uint32_t)(h * 64 + c * 16);
+              tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
+              if (P.x3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+            }
+          }
+        } else {   // K_LAST: d1 = D * 1[a_1 > 0], summed over the rows of each pair present in the tile (K2)
+          for (int64_t ps = p_first; ps <= p_last; ++ps) {
+            const bool mine = pr == ps;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t rr[32];
+              tmem_ld32(lane_addr + TMEM_D + (uint32_t)(h * 128 + c * 32), rr);
+              const uint32_t bits = mine ? S.mask[sgm.half * 8 + h * 4 + c][row] : 0u;
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? __uint_as_float(rr[i]) : 0.f;
+              S.red[q][h * 128 + c * 32 + lane] = warp_transpose_sum(v, lane);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            {
+              const float s = (S.red[0][tid] + S.red[1][tid]) + (S.red[2][tid] + S.red[3][tid]);
+              P.part[(ps + tile) * P.H1 + sgm.half * 256 + tid] = s;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+          }
+        }
+        if (!last_seg) signal_a();
+      }
+      (void)dl0; (void)dl1; (void)dl2;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// K2 tail: dUp[p,:] = sum over the tiles covering pair p of part[p + tile,:], ascending tile order.
+__global__ void reduce_slots_kernel(float* __restrict__ dUp, const float* __restrict__ part, int64_t n_pairs, int G, int H1) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pairs * H1) return;
+  int64_t p = idx / H1;
+  int c = (int)(idx % H1);
+  int64_t t0 = (p * G) / TILE_M, t1 = ((p + 1) * G - 1) / TILE_M;
+  float s = 0.f;
+  for (int64_t t = t0; t <= t1; ++t) s += part[(p + t) * H1 + c];
+  dUp[idx] = s;
+}
+__global__ void reduce_score_slots_kernel(float* __restrict__ out, const float* __restrict__ part, int64_t n_pairs, int G) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  int64_t t0 = (p * G) / TILE_M, t1 = ((p + 1) * G - 1) / TILE_M;
+  float s = 0.f;
+  for (int64_t t = t0; t <= t1; ++t) s += part[p + t];
+  out[p] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight image
+// ---------------------------------------------------------------------------------------------
+struct PackSeg { const float* src; int ld; int k0; int n_valid; int n_rows; uint32_t img_off; };
+
+// one thread per 16-byte chunk (8 bf16) of a tile
+__global__ void pack_tc_kernel(uint8_t* __restrict__ img, PackSeg ps) {
+  const int tile_bytes = ps.n_rows * 128;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunks_per_tile = ps.n_rows * 8;
+  if (idx >= 8 * chunks_per_tile) return;               // 4 k-blocks x (hi, lo)
+  const int tl = idx / chunks_per_tile, rem = idx % chunks_per_tile;
+  const int kb = tl >> 1, part = tl & 1;
+  const int n = rem / 8, j = rem % 8;
+  __nv_bfloat16 out[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float w = n < ps.n_valid ? ps.src[(int64_t)n * ps.ld + ps.k0 + kb * KBLK + j * 8 + e] : 0.f;
+    __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    out[e] = part == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+  }
+  // 128B swizzle: 16-byte chunk j of row n lands at chunk (j ^ (n & 7))
+  uint8_t* dst = img + ps.img_off + (size_t)tl * tile_bytes + (size_t)n * 128 + ((j ^ (n & 7)) * 16);
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
+}
+
+struct Plan { int n_seg; Seg seg[MAX_SEG]; PackSeg pack[MAX_SEG]; size_t bytes; };
+
+// Segment list of one tile (see the kernel header).  H1 = 256: 15 segments; H1 = 512: 17.
+Plan make_plan(const dgdm_dyn_weights* w, int H1) {
+  Plan pl{};
+  size_t off = 0;
+  auto add = [&](int kind, int layer, int half, int accum, const float* src, int ld, int k0, int n_valid, int n_rows) {
+    Seg& s = pl.seg[pl.n_seg];
+    s.img_off = (uint32_t)off; s.n_rows = (uint16_t)n_rows; s.kind = (uint8_t)kind; s.layer = (uint8_t)layer;
+    s.half = (uint8_t)half; s.accum = (uint8_t)accum;
+    pl.pack[pl.n_seg] = PackSeg{src, ld, k0, n_valid, n_rows, (uint32_t)off};
+    off += (size_t)8 * n_rows * 128;
+    ++pl.n_seg;
+  };
+  // forward, trunk layer index 1..7 = reference layers 2..8 (mask row `layer`, bias `layer-1`)
+  if (H1 == 512) {
+    add(K_MID, 1, 0, 0, w ? w->wl[0] : nullptr, 512, 0, 256, 256);
+    add(K_FWD, 1, 0, 1, w ? w->wl[0] : nullptr, 512, 256, 256, 256);
+  } else {
+    add(K_FWD, 1, 0, 0, w ? w->wl[0] : nullptr, 256, 0, 256, 256);
+  }
+  for (int l = 2; l <= 7; ++l) add(K_FWD, l, 0, 0, w ? w->wl[l - 1] : nullptr, 256, 0, 256, 256);
+  add(K_OUT, 0, 0, 0, w ? w->w_out : nullptr, 256, 0, 3, 16);
+  // backward: B operand = W_l^T rows; after layer index l the mask of layer l-1 applies
+  for (int l = 7; l >= 2; --l) add(K_BWD, l - 1, 0, 0, w ? w->wl_t[l - 1] : nullptr, 256, 0, 256, 256);
+  add(K_LAST, 0, 0, 0, w ? w->wl_t[0] : nullptr, 256, 0, 256, 256);
+  if (H1 == 512) add(K_LAST, 0, 1, 0, w ? w->wl_t[0] + 256 * 256 : nullptr, 256, 0, 256, 256);
+  pl.bytes = off;
+  return pl;
+}
+
+size_t smem_bytes() { return 1024 + (size_t)NSTAGE * WTILE_BYTES + sizeof(Smem); }
+
+}  // namespace
+
+size_t tc_trunk_workspace_bytes(int H1, int64_t n_pairs, int G) {
+  int64_t n_tiles = (n_pairs * G + TILE_M - 1) / TILE_M;
+  int64_t slots = n_pairs + n_tiles;
+  return align_up((size_t)slots * H1 * sizeof(float), 256) + align_up((size_t)slots * sizeof(float), 256) + 256;
+}
+
+int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const float* V, int n_designs, int n_obj,
+             int opd, const int32_t* pair_object, int G, const dgdm_objective* obj, bool backward, float* dUp,
+             float* score_sum, float* logits, void* ws, size_t ws_bytes, int precision, cudaStream_t s) {
+  const int H1 = w->H1;
+  const int64_t n_pairs = (int64_t)n_designs * opd;
+  const int64_t n_rows = n_pairs * G;
+  const int64_t n_tiles = (n_rows + TILE_M - 1) / TILE_M;
+  DGDM_CHECK_ARG(n_tiles < (1ll << 30), "tc_trunk: too many tiles");
+  Arena ar(ws, ws_bytes);
+  float* part = ar.take<float>((size_t)(n_pairs + n_tiles) * H1);
+  float* score_part = ar.take<float>((size_t)(n_pairs + n_tiles));
+  int* err = ar.take<int>(1);
+  if (!ar.ok) { set_error("tc_trunk: workspace too small"); return DGDM_EWORKSPACE; }
+
+  static thread_local int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    DGDM_CUDA(cudaGetDevice(&dev));
+    DGDM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  }
+  Plan pl = make_plan(w, H1);
+  TcParams P{};
+  P.img = (const uint8_t*)w->tc_image;
+  P.U = U; P.Cst = Cst; P.V = V;
+  for (int i = 0; i < 7; ++i) P.bias[i] = w->bl[i];
+  P.w_out = w->w_out; P.b_out = w->b_out;
+  P.pair_object = pair_object;
+  P.part = part; P.score_part = score_part; P.logits = logits; P.err = err;
+  P.obj = *obj;
+  P.n_rows = n_rows; P.n_tiles = (int)n_tiles; P.G = G; P.H1 = H1; P.opd = opd; P.n_designs = n_designs; P.n_obj = n_obj;
+  P.x3 = precision == DGDM_PREC_BF16X3; P.backward = backward;
+  // forward only stops after the output layer
+  int n_seg = pl.n_seg;
+  if (!backward) { n_seg = 0; while (pl.seg[n_seg].kind != K_OUT) ++n_seg; ++n_seg; }
+  P.n_seg = n_seg;
+  for (int i = 0; i < n_seg; ++i) P.seg[i] = pl.seg[i];
+
+  DGDM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
+  const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+  tc_trunk_kernel<<<grid, NTHREADS, smem_bytes(), s>>>(P);
+  DGDM_LAUNCH_CHECK();
+  if (backward) {
+    reduce_slots_kernel<<<(unsigned)((n_pairs * H1 + 255) / 256), 256, 0, s>>>(dUp, part, n_pairs, G, H1);
+  } else {
+    reduce_score_slots_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(score_sum, score_part, n_pairs, G);
+  }
+  DGDM_LAUNCH_CHECK();
+  return DGDM_OK;
+}
+
 }  // namespace dgdm
-extern "C" size_t dgdm_dyn_tc_image_bytes(int32_t) { return 256; }
-extern "C" int dgdm_dyn_pack_tc(const dgdm_dyn_weights*, void*, void*) {
-  dgdm::set_error("tensor-core trunk not built");
-  return DGDM_EUNSUPPORTED;
+
+extern "C" size_t dgdm_dyn_tc_image_bytes(int32_t H1) {
+  if (H1 != 256 && H1 != 512) return 0;
+  return dgdm::make_plan(nullptr, H1).bytes;
+}
+
+extern "C" int dgdm_dyn_pack_tc(const dgdm_dyn_weights* w, void* tc_image, void* stream) {
+  using namespace dgdm;
+  DGDM_CHECK_ARG(w && tc_image, "dgdm_dyn_pack_tc: null pointer");
+  DGDM_CHECK_ARG(w->H1 == 256 || w->H1 == 512, "dgdm_dyn_pack_tc: H1=%d unsupported", w->H1);
+  DGDM_CHECK_ARG(((uintptr_t)tc_image) % 128 == 0, "dgdm_dyn_pack_tc: image must be 128-byte aligned");
+  Plan pl = make_plan(w, w->H1);
+  for (int i = 0; i < pl.n_seg; ++i) {
+    const int chunks = 8 * pl.pack[i].n_rows * 8;
+    pack_tc_kernel<<<(chunks + 255) / 256, 256, 0, (cudaStream_t)stream>>>((uint8_t*)tc_image, pl.pack[i]);
+    DGDM_LAUNCH_CHECK();
+  }
+  return DGDM_OK;
 }
