@@ -55,6 +55,8 @@ EXPORTS = {
     "dgdm_last_error": (C.c_char_p, []),
     "dgdm_abi_version": (C.c_int, []),
     "dgdm_launch_count": (C.c_uint64, []),
+    "dgdm_trunk_timing": (C.c_int, [C.c_int32]),
+    "dgdm_trunk_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dgdm_ddim_guided_update": (C.c_int, [fp, fp, fp, fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                           C.c_float, C.c_int, fp]),
     "dgdm_dyn_tc_image_bytes": (C.c_size_t, [C.c_int32]),

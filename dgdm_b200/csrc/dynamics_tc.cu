@@ -27,6 +27,8 @@
 // the same fp32 accumulator: ~2^-16 relative product error, fp32-grade (<=1e-3 end to end).  BF16 issues one.
 #include <cuda_bf16.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace dgdm {
@@ -532,6 +534,15 @@ Plan make_plan(const dgdm_dyn_weights* w, int H1) {
 
 size_t smem_bytes() { return 1024 + (size_t)NSTAGE * WTILE_BYTES + sizeof(Smem); }
 
+// event-pair timing of the trunk kernel (bench.py roofline)
+struct Timing {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // start, stop, start, stop, ...
+  size_t used = 0;
+  int64_t rows = 0;
+};
+Timing g_timing;
+
 }  // namespace
 
 size_t tc_trunk_workspace_bytes(int H1, int64_t n_pairs, int G) {
@@ -580,8 +591,18 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
 
   DGDM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_timing.on) {
+    if (g_timing.used + 2 > g_timing.ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; DGDM_CUDA(cudaEventCreate(&e)); g_timing.ev.push_back(e); }
+    }
+    e0 = g_timing.ev[g_timing.used]; e1 = g_timing.ev[g_timing.used + 1];
+    g_timing.used += 2; g_timing.rows += n_rows;
+    DGDM_CUDA(cudaEventRecord(e0, s));
+  }
   tc_trunk_kernel<<<grid, NTHREADS, smem_bytes(), s>>>(P);
   DGDM_LAUNCH_CHECK();
+  if (e1) DGDM_CUDA(cudaEventRecord(e1, s));
   if (backward) {
     reduce_slots_kernel<<<(unsigned)((n_pairs * H1 + 255) / 256), 256, 0, s>>>(dUp, part, n_pairs, G, H1);
   } else {
@@ -592,6 +613,27 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
 }
 
 }  // namespace dgdm
+
+extern "C" int dgdm_trunk_timing(int32_t enable) {
+  dgdm::g_timing.on = enable != 0;
+  dgdm::g_timing.used = 0;
+  dgdm::g_timing.rows = 0;
+  return DGDM_OK;
+}
+
+extern "C" int dgdm_trunk_timing_read(double* total_ms, int64_t* launches, int64_t* rows) {
+  using namespace dgdm;
+  DGDM_CHECK_ARG(total_ms && launches && rows, "dgdm_trunk_timing_read: null pointer");
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < g_timing.used; i += 2) {
+    DGDM_CUDA(cudaEventSynchronize(g_timing.ev[i + 1]));
+    float ms = 0.f;
+    DGDM_CUDA(cudaEventElapsedTime(&ms, g_timing.ev[i], g_timing.ev[i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot; *launches = (int64_t)(g_timing.used / 2); *rows = g_timing.rows;
+  return DGDM_OK;
+}
 
 extern "C" size_t dgdm_dyn_tc_image_bytes(int32_t H1) {
   if (H1 != 256 && H1 != 512) return 0;

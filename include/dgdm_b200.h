@@ -150,6 +150,13 @@ int dgdm_dyn_score(const dgdm_dyn_weights* w, const float* x, int32_t n_designs,
                    const dgdm_objective* objective, float* scores, float* logits, void* workspace,
                    size_t workspace_bytes, int32_t precision, void* stream);
 
+/* Optional CUDA-event timing of the dominant kernel (the fused tensor-core trunk), used by bench.py for the
+ * roofline line.  enable != 0 resets the counters and makes every subsequent launch of that kernel record an
+ * event pair on its own stream; read() synchronises those events and returns the summed device time, the number
+ * of launches and the number of guidance rows they processed. */
+int dgdm_trunk_timing(int32_t enable);
+int dgdm_trunk_timing_read(double* total_ms, int64_t* launches, int64_t* rows);
+
 /* ------------------------------------------------------------------------------------------------
  * K3  denoiser.  Replaces ConditionalUnet1D.forward (generator/diffusion_utils.py:238-285) for the one
  * configuration the reference builds (generator/train.py:80): input_dim 1, down_dims [128,256],
