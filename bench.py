@@ -36,9 +36,21 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 FLOP_PER_ROW_2D = 2 * 2 * (7 * 256 * 256 + 256 * 3)          # 1 838 080, SURVEY.md §8d
+FLOP_PER_ROW_3D = 2 * 2 * (512 * 256 + 6 * 256 * 256 + 256 * 3)   # 2 100 224
 N_OBJ, N_CAND, GRID, NPOS, P = 64, 256, 36, 5, 14
+MODE = "point"
 T_TRAIN, T_INF = 15, 5
 OBJECTIVE = "rotate_clockwise"
+WORKLOAD = "C2 (BASELINE.json configs[1])"
+
+
+def select_workload(name):
+    """c2 (default, the metric's configuration) or c3 (BASELINE.json configs[2]: 3D point clouds, 128 candidates,
+    stock 3D pose grid 45 x 5 x 5; object count unspecified there -> 64)."""
+    global N_OBJ, N_CAND, GRID, NPOS, P, MODE, WORKLOAD
+    if name == "c3":
+        N_OBJ, N_CAND, GRID, NPOS, P, MODE = 64, 128, 45, 5, 42, "point_3d"
+        WORKLOAD = "C3 (BASELINE.json configs[2])"
 
 
 def peaks():
@@ -97,6 +109,9 @@ def oracle_sampler(n_obj):
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import dgdm_oracle as orc
     from dgdm_b200 import synthetic as syn
+    if MODE == "point_3d":
+        return orc.OracleSampler("point_3d", syn.unet1d_state_dict(0), syn.dynamics3d_state_dict(0), syn.objects_3d(n_obj),
+                                 GRID, NPOS, T_TRAIN, T_INF, sub_batch_size=512, fps_start=syn.fps_starts(n_obj))
     return orc.OracleSampler("point", syn.unet1d_state_dict(0), syn.dynamics2d_state_dict(0), syn.objects_2d(n_obj),
                              GRID, NPOS, T_TRAIN, T_INF)
 
@@ -120,7 +135,8 @@ def run_reference(args):
     import torch
     from dgdm_b200 import synthetic as syn
     torch.set_num_threads(os.cpu_count() or 1)
-    n_obj_s, b_s = 1, 32                                  # bounded sample of C2: 1 object x 32 candidates x 900 rows
+    select_workload(args.workload)
+    n_obj_s, b_s = 1, (32 if MODE == "point" else 8)      # bounded sample: 1 object x 32 (8) candidates x G rows
     samp = oracle_sampler(n_obj_s)
     noise = syn.initial_noise(b_s, P)
     for _ in range(max(0, args.warmup)):
@@ -142,7 +158,7 @@ def run_reference(args):
 
 
 def workload_config(n_gpus, precision):
-    return {"workload": f"C2 (BASELINE.json configs[1]): 2D guided sampling, {N_OBJ} objects/GPU x {N_CAND} candidates x "
+    return {"workload": f"{WORKLOAD}: {'3D' if MODE == 'point_3d' else '2D'} guided sampling, {N_OBJ} objects/GPU x {N_CAND} candidates x "
                         f"{GRID} orientations x {NPOS}x{NPOS} positions = {GRID * NPOS * NPOS} pose rows/candidate, "
                         f"{T_INF} DDIM steps of {T_TRAIN}, objective {OBJECTIVE}, + scoring pass + best-of-N",
             "objects_per_gpu": N_OBJ, "candidates": N_CAND, "pose_rows": GRID * NPOS * NPOS, "ddim_steps": T_INF,
@@ -159,7 +175,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -187,11 +205,14 @@ def main():
     # ---- workload: this rank's shard of the 64*world objects -------------------------------------------------
     n_obj_global = N_OBJ * world
     lo, hi = D.shard_range(n_obj_global, world, rank)
-    objs_host = syn.objects_2d(n_obj_global)[lo:hi].contiguous().pin_memory()
+    is3d = MODE == "point_3d"
+    objs_host = (syn.objects_3d(n_obj_global) if is3d else syn.objects_2d(n_obj_global))[lo:hi].contiguous().pin_memory()
+    fps_host = syn.fps_starts(n_obj_global)[lo:hi].contiguous() if is3d else None
     noise_host = syn.initial_noise(N_CAND, P).pin_memory()
-    dm = Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(T_TRAIN), T_INF, mode="point", num_points=P,
-                   classifier_model=syn.dynamics2d_state_dict(0), grid_size=GRID, num_pos=NPOS,
-                   object_vertices=objs_host, object_ids=list(range(lo, hi)), precision=args.precision, device=dev)
+    dm = Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(T_TRAIN), T_INF, mode=MODE, num_points=P,
+                   classifier_model=syn.dynamics3d_state_dict(0) if is3d else syn.dynamics2d_state_dict(0),
+                   grid_size=GRID, num_pos=NPOS, object_vertices=objs_host, object_ids=list(range(lo, hi)),
+                   fps_starts=fps_host, precision=args.precision, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     noise_dev = noise_host.to(dev)
 
@@ -204,7 +225,7 @@ def main():
     def one_pass_e2e():
         # host -> device: this pass's inputs from pinned memory; device -> host: designs, scores, best ids
         nz = noise_host.to(dev, non_blocking=True)
-        dm.set_objects(objs_host.to(dev, non_blocking=True))
+        dm.set_objects(objs_host.to(dev, non_blocking=True), fps_host)      # 3D: PointNet++ (K5) runs here, every pass
         local = dm.guided_sample(0, N_CAND, nz, opt_obj=OBJECTIVE)
         g = D.gather_per_object_results(local, n_obj_global, gather_designs=False)
         for k in ("scores", "best_ids", "best_scores"):
@@ -259,7 +280,8 @@ def main():
         G = GRID * NPOS * NPOS
         bwd_rows = (hi - lo) * N_CAND * G * T_INF * args.steps
         fwd_rows = int(nrows.value) - bwd_rows                      # scoring-pass rows (forward only: half the FLOPs)
-        flops = bwd_rows * FLOP_PER_ROW_2D + max(0, fwd_rows) * (FLOP_PER_ROW_2D // 2)
+        fpr = FLOP_PER_ROW_3D if is3d else FLOP_PER_ROW_2D
+        flops = bwd_rows * fpr + max(0, fwd_rows) * (fpr // 2)
         achieved = flops / (tot.value / 1e3) / 1e12 if tot.value > 0 else 0.0
         peak = pk["bf16_sustained"] / (3.0 if x3 else 1.0)
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -270,12 +292,13 @@ def main():
                     "launches": int(nl.value), "avg_launch_ms": tot.value / max(1, nl.value),
                     "kernel_share_of_step": tot.value / ms,
                     "executed_tflops": achieved * (3.0 if x3 else 1.0),
-                    "flop_per_row": FLOP_PER_ROW_2D}
+                    "flop_per_row": fpr}
         cpu = None
         if not args.no_cpu_baseline and args.gpus == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             samp = oracle_sampler(1)
-            nz = syn.initial_noise(32, P)
+            nb = 32 if not is3d else 8
+            nz = syn.initial_noise(nb, P)
             t0 = time.perf_counter()
             reps = 0
             while True:
@@ -284,8 +307,9 @@ def main():
                 if time.perf_counter() - t0 > 10.0 or reps >= 8:
                     break
             dt = time.perf_counter() - t0
-            cpu = {"value": 32 * reps / dt, "unit": "designs/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"{reps} x (1 object x 32 candidates x {G} pose rows x {T_INF} steps + scoring) of the same workload"}
+            cpu = {"value": nb * reps / dt, "unit": "designs/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{reps} x (1 object x {nb} candidates x {G} pose rows x {T_INF} steps + scoring) of the same workload"
+                             + (" (PointNet++ hoisted to once per object, unlike the as-written reference)" if is3d else "")}
         h2d = noise_host.numel() * 4 + objs_host.numel() * 4
         d2h = sum(v.numel() * v.element_size() for v in out_host.values())
         line = {"metric": "guided designs/sec", "value": value, "unit": "designs/s", "n_gpus": world, "steps": args.steps,

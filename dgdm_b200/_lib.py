@@ -43,7 +43,7 @@ class UnetResBlock(C.Structure):
 class UnetWeights(C.Structure):
     _fields_ = ([(n, fp) for n in ("se_w0", "se_b0", "se_w1", "se_b1")] + [("blocks", UnetResBlock * 8)] +
                 [(n, fp) for n in ("down_w", "down_b", "up_w", "up_b", "fin_w", "fin_b", "fin_gn_w", "fin_gn_b",
-                                   "out_w", "out_b")])
+                                   "out_w", "out_b", "tc_image")])
 
 
 class PointNet2Weights(C.Structure):
@@ -70,7 +70,12 @@ EXPORTS = {
                                  C.POINTER(PoseGrid), C.POINTER(Objective), fp, fp, fp, C.c_size_t, C.c_int32, fp]),
     "dgdm_unet1d_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "dgdm_unet1d_forward": (C.c_int, [C.POINTER(UnetWeights), fp, C.c_int32, C.c_int32, C.c_int32, fp, fp,
-                                      C.c_size_t, fp]),
+                                      C.c_size_t, C.c_int32, fp]),
+    "dgdm_unet_tc_image_bytes": (C.c_size_t, [C.POINTER(UnetWeights)]),
+    "dgdm_unet_pack_tc": (C.c_int, [C.POINTER(UnetWeights), fp, fp]),
+    "dgdm_linear_tc_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "dgdm_linear_tc": (C.c_int, [fp, C.c_int64, fp, fp, fp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, fp, C.c_size_t, fp]),
     "dgdm_pointnet2_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "dgdm_pointnet2_encode": (C.c_int, [C.POINTER(PointNet2Weights), fp, C.c_int32, C.c_int32, fp, fp, fp,
                                         C.c_size_t, fp]),

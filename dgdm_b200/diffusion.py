@@ -141,7 +141,8 @@ class Diffusion:
         self.sub_batch_size = sub_batch_size                      # accepted, unused: rows never hit HBM
         with torch.cuda.device(self.device):
             self.unet = noise_pred_net if isinstance(noise_pred_net, UnetPack) else \
-                UnetPack(load_unet_state_dict(noise_pred_net), self.device)
+                UnetPack(load_unet_state_dict(noise_pred_net), self.device,
+                         build_tc=self.precision != _lib.PREC_FP32_SIMT)
             self.dyn: Optional[DynamicsPack] = None
             self.pn2: Optional[PointNet2Pack] = None
             if class_cond:
@@ -232,7 +233,8 @@ class Diffusion:
         ws = self._workspace("unet", self.lib.dgdm_unet1d_workspace_bytes(n, P))
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dgdm_unet1d_forward(C.byref(self.unet.struct), x.data_ptr(), n, P, t, eps.data_ptr(),
-                                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "dgdm_unet1d_forward")
+                                                    ws.data_ptr(), ws.numel(), self.precision, _lib.stream_ptr()),
+                       "dgdm_unet1d_forward")
         return eps.reshape(sample.shape)
 
     def _grid(self, ori_range: Sequence[float], profile: bool = False) -> _lib.PoseGrid:

@@ -214,8 +214,9 @@ class PointNet2Pack:
 
 
 class UnetPack:
-    def __init__(self, sd, device):
+    def __init__(self, sd, device, build_tc: bool = True):
         self.host = fold_unet(sd)
+        self.device = torch.device(device)
         dev = lambda v: None if v is None else v.to(device)
         self.t = {k: dev(v) for k, v in self.host.items() if k != "blocks"}
         self.blocks = [{k: (dev(v) if isinstance(v, torch.Tensor) else v) for k, v in b.items()}
@@ -228,4 +229,17 @@ class UnetPack:
             for k, v in b.items():
                 if k not in ("cin", "cout"):
                     setattr(s.blocks[i], k, None if v is None else v.data_ptr())
+        s.tc_image = None
         self.struct = s
+        self.tc_image: Optional[torch.Tensor] = None
+        if build_tc:
+            self.build_tc_image()
+
+    def build_tc_image(self):
+        l = _lib.lib()
+        n = l.dgdm_unet_tc_image_bytes(C.byref(self.struct))
+        self.tc_image = torch.empty(n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(l.dgdm_unet_pack_tc(C.byref(self.struct), self.tc_image.data_ptr(), _lib.stream_ptr()),
+                       "dgdm_unet_pack_tc")
+        self.struct.tc_image = self.tc_image.data_ptr()

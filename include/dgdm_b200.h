@@ -180,12 +180,19 @@ typedef struct dgdm_unet_weights {
                                              * even outputs use taps k=3,1, odd outputs k=2,0      */
   const float* fin_w;  const float* fin_b;  const float* fin_gn_w; const float* fin_gn_b; /* final_conv.0 */
   const float* out_w;  const float* out_b;  /* final_conv.1 [1][128],[1]                           */
+  const void* tc_image;                     /* tensor-core weight image (dgdm_unet_pack_tc) or NULL */
 } dgdm_unet_weights;
 
+/* Tensor-core image of every conv whose contraction is tcgen05-eligible (Cin % 64 == 0): bf16 hi/lo split,
+ * 64-wide k-blocks, 128B-swizzled K-major tiles. */
+size_t dgdm_unet_tc_image_bytes(const dgdm_unet_weights* w);
+int dgdm_unet_pack_tc(const dgdm_unet_weights* w, void* image, void* stream);
+
 size_t dgdm_unet1d_workspace_bytes(int32_t n, int32_t P);
-/* x [n,P] (the reference's (B,P,1)), t integer timestep, eps [n,P] (out). */
+/* x [n,P] (the reference's (B,P,1)), t integer timestep, eps [n,P] (out).  precision: DGDM_PREC_* -- the
+ * tensor-core modes run the implicit-GEMM convs on tcgen05 (3 bf16 MMAs per product in BF16X3). */
 int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, int32_t n, int32_t P, int32_t t, float* eps,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        void* workspace, size_t workspace_bytes, int32_t precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5  PointNet++ SSG object encoder, once per object.  Replaces PointNet2.forward
@@ -218,6 +225,11 @@ int dgdm_best_of_n(const float* scores, int32_t n_obj, int32_t n_cand, int32_t k
  */
 int dgdm_linear_f32(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
                     int64_t M, int32_t N, int32_t K, int32_t relu, void* stream);
+/* Same contraction on the tcgen05 path (K %% 64 == 0, N in {128,256}); packs W into the workspace first. */
+size_t dgdm_linear_tc_workspace_bytes(int32_t N, int32_t K);
+int dgdm_linear_tc(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int64_t M,
+                   int32_t N, int32_t K, int32_t relu, int32_t precision, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 #ifdef __cplusplus
 }

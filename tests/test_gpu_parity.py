@@ -141,28 +141,53 @@ def test_linear_f32(M, N, K):
         assert rel(C, want) < 1e-6
 
 
+@pytest.mark.parametrize("precision", TC_MODES)
+@pytest.mark.parametrize("M,N,K", [(1, 128, 64), (130, 256, 640), (1000, 128, 1280), (257, 256, 2560), (128, 256, 128)])
+def test_linear_tc(M, N, K, precision):
+    """tcgen05 GEMM with on-the-fly bf16 hi/lo operand split vs float64."""
+    from dgdm_b200 import _lib
+    rs = np.random.RandomState(M + N + K)
+    A = torch.from_numpy(rs.randn(M, K).astype(np.float32)); W = torch.from_numpy((rs.randn(N, K) / np.sqrt(K)).astype(np.float32))
+    b = torch.from_numpy(rs.randn(N).astype(np.float32))
+    Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
+    C = torch.empty(M, N, device="cuda")
+    l = _lib.lib()
+    ws = torch.empty(l.dgdm_linear_tc_workspace_bytes(N, K), dtype=torch.uint8, device="cuda")
+    for relu in (0, 1):
+        _lib.check(l.dgdm_linear_tc(Ad.data_ptr(), K, Wd.data_ptr(), bd.data_ptr(), C.data_ptr(), N, M, N, K, relu,
+                                    _lib.PRECISIONS[precision], ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        want = torch.nn.functional.linear(A.double(), W.double(), b.double())
+        want = torch.relu(want) if relu else want
+        assert rel(C, want) < (2e-5 if precision == "fp32" else 6e-3), rel(C, want)
+
+
 # ---------------------------------------------------------------------------------------------- K3
-def test_unet_golden(g2, g3):
-    dm = make2d("fp32_simt", torch.from_numpy(g2["objects"]), int(g2["grid_size"]), int(g2["num_pos"]))
+UNET_TOL = {"fp32_simt": 1e-4, "fp32": 1e-3, "bf16": 2e-2}
+
+
+@pytest.mark.parametrize("precision", ALL_MODES)
+def test_unet_golden(g2, g3, precision):
+    dm = make2d(precision, torch.from_numpy(g2["objects"]), int(g2["grid_size"]), int(g2["num_pos"]))
     for g in (g2, g3):
         x = torch.from_numpy(g["noise"])
         for t in (12, 0):
             got = dm.noise_pred_net(x.cuda(), torch.full((x.shape[0],), t, dtype=torch.int64))
             assert got.shape == x.shape
-            assert rel(got, g[f"unet_t{t}"]) < 1e-4, (t, rel(got, g[f"unet_t{t}"]))
+            assert rel(got, g[f"unet_t{t}"]) < UNET_TOL[precision], (t, rel(got, g[f"unet_t{t}"]))
 
 
+@pytest.mark.parametrize("precision", ALL_MODES)
 @pytest.mark.parametrize("n,P", [(1, 14), (300, 14), (4100, 14), (130, 42)])
-def test_unet_vs_oracle(n, P, g2):
-    dm = make2d("fp32_simt", torch.from_numpy(g2["objects"]), 2, 1)
+def test_unet_vs_oracle(n, P, g2, precision):
+    dm = make2d(precision, torch.from_numpy(g2["objects"]), 2, 1)
     x = syn.initial_noise(n, P, seed=5)
     with torch.no_grad():
         want = orc.unet1d_forward(syn.unet1d_state_dict(0), x, torch.full((n,), 9, dtype=torch.int64))
     got = dm.noise_pred_net(x.cuda(), 9)
-    assert rel(got, want) < 1e-4
+    assert rel(got, want) < UNET_TOL[precision], rel(got, want)
     # worst single sample, too
     per = (got.cpu() - want).reshape(n, -1).norm(dim=1) / want.reshape(n, -1).norm(dim=1)
-    assert float(per.max()) < 1e-3
+    assert float(per.max()) < 10 * UNET_TOL[precision]
 
 
 # ---------------------------------------------------------------------------------------------- K1+K2

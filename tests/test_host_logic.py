@@ -161,7 +161,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.DynWeights) == 16 + 20 * 8 + 21 * 8 + 3 * 8
     assert C.sizeof(_lib.PoseGrid) == 20 and C.sizeof(_lib.Objective) == 24
     assert C.sizeof(_lib.UnetResBlock) == 8 + 12 * 8
-    assert C.sizeof(_lib.UnetWeights) == 4 * 8 + 8 * C.sizeof(_lib.UnetResBlock) + 10 * 8
+    assert C.sizeof(_lib.UnetWeights) == 4 * 8 + 8 * C.sizeof(_lib.UnetResBlock) + 11 * 8
     assert C.sizeof(_lib.PointNet2Weights) == 80
 
 
