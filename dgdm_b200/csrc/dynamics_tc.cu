@@ -125,6 +125,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// Issue only; the registers may be read after tmem_ld_wait32 (which names them so the compiler keeps the order).
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -156,14 +175,17 @@ __device__ __forceinline__ int pair_obj(int64_t p, int opd, int n_designs, int n
 }
 
 // Split 32 fp32 values into packed bf16 hi (and lo = rn(v - hi)) pairs; element 2i in the low half.
+template <bool X3>
 __device__ __forceinline__ void split_pack(const float (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    float2 hf = __bfloat1622float2(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
     hi[i] = *reinterpret_cast<uint32_t*>(&h);
-    lo[i] = *reinterpret_cast<uint32_t*>(&l);
+    if (X3) {
+      float2 hf = __bfloat1622float2(h);
+      __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+      lo[i] = *reinterpret_cast<uint32_t*>(&l);
+    }
   }
 }
 
@@ -194,6 +216,7 @@ struct Smem {
   uint32_t mask[MASK_WORDS][TILE_M];
 };
 
+template <bool X3>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // weight ring first (1024-byte aligned for the 128B swizzle), bookkeeping after
@@ -221,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
   const uint32_t tmem = S.tmem_base;
 
   const int tiles_mine = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tiles_per_seg = P.x3 ? 8 : 4;       // weight tiles per segment: 4 k-blocks x (hi [, lo])
+  const int tiles_per_seg = X3 ? 8 : 4;       // weight tiles per segment: 4 k-blocks x (hi [, lo])
 
   if (warp == 8) {
     // =============================== producer ===============================
@@ -233,7 +256,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           const uint32_t tile_bytes = (uint32_t)sgm.n_rows * 128u;
           for (int j = 0; j < tiles_per_seg; ++j) {
             // image order inside a segment: kb0.hi, kb0.lo, kb1.hi, kb1.lo, ...
-            const int kb = P.x3 ? (j >> 1) : j, part = P.x3 ? (j & 1) : 0;
+            const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;
             mbar_wait(&S.empty[stage], phase ^ 1, P.err, 1);
             mbar_arrive_expect_tx(&S.full[stage], tile_bytes);
             bulk_g2s(ring + stage * WTILE_BYTES, P.img + sgm.img_off + (size_t)(kb * 2 + part) * tile_bytes, tile_bytes,
@@ -256,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           tc_fence_after();
           uint32_t accum = sgm.accum;
           for (int j = 0; j < tiles_per_seg; ++j) {
-            const int kb = P.x3 ? (j >> 1) : j, part = P.x3 ? (j & 1) : 0;
+            const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;
             mbar_wait(&S.full[stage], phase, P.err, 3);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(ring + stage * WTILE_BYTES);
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
               const uint32_t a_col = (uint32_t)(kb * (KBLK / 2) + ks * 8);     // 16 bf16 = 8 TMEM columns
               tc_mma_ts(tmem + TMEM_D, tmem + TMEM_A_HI + a_col, bdesc, idesc, accum);
               accum = 1;
-              if (P.x3 && part == 0) tc_mma_ts(tmem + TMEM_D, tmem + TMEM_A_LO + a_col, bdesc, idesc, 1);
+              if (X3 && part == 0) tc_mma_ts(tmem + TMEM_D, tmem + TMEM_A_LO + a_col, bdesc, idesc, 1);
             }
             tc_commit(&S.empty[stage]);           // stage reusable once these MMAs have read it
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -323,10 +346,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           }
           S.mask[kh * 8 + h * 4 + c][row] = bits;
           uint32_t hi[16], lo[16];
-          split_pack(v, hi, lo);
+          split_pack<X3>(v, hi, lo);
           const uint32_t acol = (uint32_t)(h * 64 + c * 16);
           tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
-          if (P.x3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+          if (X3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
         }
       };
       auto signal_a = [&]() {
@@ -352,17 +375,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         } else if (sgm.kind == K_FWD || sgm.kind == K_BWD) {
           // FWD: a = relu(D + b), record sign bits of layer `layer`.   BWD: d = D * 1[a_{layer} > 0].
           const int mbase = sgm.layer == 0 ? 0 : l1_words + (sgm.layer - 1) * 8;   // mask row of trunk layer index
-#pragma unroll 1
+          // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed
+          uint32_t rr[2][32];
+          tmem_ld32_async(lane_addr + TMEM_D + (uint32_t)(h * 128), rr[0]);
+#pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint32_t rr[32];
-            tmem_ld32(lane_addr + TMEM_D + (uint32_t)(h * 128 + c * 32), rr);
+            tmem_ld_wait32(rr[c & 1]);
+            if (c + 1 < 4) tmem_ld32_async(lane_addr + TMEM_D + (uint32_t)(h * 128 + (c + 1) * 32), rr[(c + 1) & 1]);
             float v[32];
             if (sgm.kind == K_FWD) {
               const float* b = &S.bias[sgm.layer - 1][h * 128 + c * 32];
               uint32_t bits = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                float z = __uint_as_float(rr[i]) + b[i];
+                float z = __uint_as_float(rr[c & 1][i]) + b[i];
                 bits |= (z > 0.f ? 1u : 0u) << i;
                 v[i] = fmaxf(z, 0.f);
               }
@@ -370,13 +396,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             } else {
               const uint32_t bits = S.mask[mbase + h * 4 + c][row];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? __uint_as_float(rr[i]) : 0.f;
+              for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? __uint_as_float(rr[c & 1][i]) : 0.f;
             }
             uint32_t hi[16], lo[16];
-            split_pack(v, hi, lo);
+            split_pack<X3>(v, hi, lo);
             const uint32_t acol = (uint32_t)(h * 64 + c * 16);
             tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
-            if (P.x3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+            if (X3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
           }
         } else if (sgm.kind == K_OUT) {
           uint32_t rr[8];
@@ -414,10 +440,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
                 v[i] = (bits >> i) & 1u ? d : 0.f;
               }
               uint32_t hi[16], lo[16];
-              split_pack(v, hi, lo);
+              split_pack<X3>(v, hi, lo);
               const uint32_t acol = (uint32_t)(h * 64 + c * 16);
               tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
-              if (P.x3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+              if (X3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
             }
           }
         } else {   // K_LAST: d1 = D * 1[a_1 > 0], summed over the rows of each pair present in the tile (K2)
@@ -570,7 +596,8 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
     int dev = 0;
     DGDM_CUDA(cudaGetDevice(&dev));
     DGDM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   }
   Plan pl = make_plan(w, H1);
   TcParams P{};
@@ -600,7 +627,8 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
     g_timing.used += 2; g_timing.rows += n_rows;
     DGDM_CUDA(cudaEventRecord(e0, s));
   }
-  tc_trunk_kernel<<<grid, NTHREADS, smem_bytes(), s>>>(P);
+  if (P.x3) tc_trunk_kernel<true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
+  else tc_trunk_kernel<false><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   DGDM_LAUNCH_CHECK();
   if (e1) DGDM_CUDA(cudaEventRecord(e1, s));
   if (backward) {

@@ -16,6 +16,8 @@ from dgdm_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32_simt": 1e-4, "fp32": 1e-3, "bf16": 2e-2}
+TC_MODES = ["fp32", "bf16"]
+ALL_MODES = ["fp32_simt"] + TC_MODES
 
 
 def tol_for(precision, G):
