@@ -21,7 +21,8 @@
 //            sign bits, convert to bf16 (hi [+ lo]) and tcgen05.st it back as the next layer's A operand.
 //            The last backward layer is reduced over the tile's rows per pair with warp shuffles and written
 //            to a per-(pair,tile) slot; a small second kernel adds the slots in fixed order (deterministic).
-// TMEM map (512 columns): A_hi [0,128) | A_lo [128,256) | D [256,512).
+// TMEM: two 256-column regions that swap roles every layer (A operand, per 64-wide k-block [hi 32 | lo 32] columns,
+// and fp32 accumulator); the epilogue rewrites the accumulator in place into the next A operand.
 //
 // Precision modes: BF16X3 splits both operands into bf16 hi + lo and issues 3 MMAs (hi*hi, lo*hi, hi*lo) into
 // the same fp32 accumulator: ~2^-16 relative product error, fp32-grade (<=1e-3 end to end).  BF16 issues one.
@@ -41,7 +42,6 @@ constexpr int NSTAGE = 5;
 constexpr int NTHREADS = 320;
 constexpr int MAX_SEG = 20;
 constexpr int MASK_WORDS = 16 + 7 * 8;         // layer 1 up to 512 wide + 7 layers of 256
-constexpr uint32_t TMEM_A_HI = 0, TMEM_A_LO = 128, TMEM_D = 256;
 
 enum { K_FWD = 0, K_MID = 1, K_OUT = 2, K_BWD = 3, K_LAST = 4 };
 
@@ -206,7 +206,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 }
 
 struct Smem {
-  uint64_t full[NSTAGE], empty[NSTAGE], a_ready, d_ready;
+  uint64_t full[NSTAGE], empty[NSTAGE], a_ready[4], d_ready;
   uint32_t tmem_base, pad_;
   float bias[7][256];
   float w_out[3][256];
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    mbar_init(&S.a_ready, 8);
+    for (int k = 0; k < 4; ++k) mbar_init(&S.a_ready[k], 8);
     mbar_init(&S.d_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -268,43 +268,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
     }
   } else if (warp == 9) {
     // =============================== MMA issuer ===============================
+    // TMEM is two 256-column regions.  During a segment the A operand lives in region `cur` (per 64-wide
+    // k-block kb: hi at [64kb, 64kb+32), lo at [64kb+32, 64kb+64)) and the accumulator in the other one.
+    // The epilogue converts the accumulator IN PLACE into the next layer's A operand, k-block by k-block,
+    // and hands each k-block over on its own mbarrier, so the next layer's MMAs start after a quarter of the
+    // epilogue instead of all of it; the roles of the two regions then swap.
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0;
       for (int t = 0; t < tiles_mine; ++t) {
+        uint32_t cur = 0;
         for (int sg = 0; sg < P.n_seg; ++sg) {
           const Seg sgm = P.seg[sg];
           const uint32_t idesc = make_idesc(sgm.n_rows);
-          mbar_wait(&S.a_ready, a_phase, P.err, 2);
-          a_phase ^= 1;
-          tc_fence_after();
+          const uint32_t a_base = tmem + cur * 256u, d_base = tmem + (cur ^ 1u) * 256u;
           uint32_t accum = sgm.accum;
           for (int j = 0; j < tiles_per_seg; ++j) {
             const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;
+            if (part == 0) {
+              mbar_wait(&S.a_ready[kb], a_phase, P.err, 2);
+              tc_fence_after();
+            }
             mbar_wait(&S.full[stage], phase, P.err, 3);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(ring + stage * WTILE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < KBLK / 16; ++ks) {
               const uint64_t bdesc = make_b_desc(b_addr + ks * 32);
-              const uint32_t a_col = (uint32_t)(kb * (KBLK / 2) + ks * 8);     // 16 bf16 = 8 TMEM columns
-              tc_mma_ts(tmem + TMEM_D, tmem + TMEM_A_HI + a_col, bdesc, idesc, accum);
+              const uint32_t a_col = (uint32_t)(kb * 64 + ks * 8);             // 16 bf16 = 8 TMEM columns
+              tc_mma_ts(d_base, a_base + a_col, bdesc, idesc, accum);
               accum = 1;
-              if (X3 && part == 0) tc_mma_ts(tmem + TMEM_D, tmem + TMEM_A_LO + a_col, bdesc, idesc, 1);
+              if (X3 && part == 0) tc_mma_ts(d_base, a_base + a_col + 32, bdesc, idesc, 1);
             }
             tc_commit(&S.empty[stage]);           // stage reusable once these MMAs have read it
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
           tc_commit(&S.d_ready);                  // accumulator complete
+          a_phase ^= 1;
+          if (sgm.kind == K_FWD || sgm.kind == K_BWD || sgm.kind == K_OUT) cur ^= 1;
         }
       }
     }
   } else {
     // =============================== epilogue warps 0..7 ===============================
-    const int q = warp & 3, h = warp >> 2;        // TMEM lane quadrant, column half
+    // warp (q, h): TMEM lane quadrant q (rows 32q..32q+31); of every 64-feature k-block it owns the 32-feature
+    // half h.  The two warps of a quadrant share lanes, so they meet on a named barrier before overwriting
+    // accumulator columns the other one still has to read.
+    const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int l1_words = P.H1 / 32;
     uint32_t d_phase = 0;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); };
 
     for (int t = 0; t < tiles_mine; ++t) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
@@ -323,12 +337,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
       int64_t last_row = (int64_t)tile * TILE_M + TILE_M - 1;
       if (last_row >= P.n_rows) last_row = P.n_rows - 1;
       const int64_t p_last = last_row / P.G;
+      uint32_t cur = 0;                            // region holding the A operand of the current segment
 
-      // layer-1 activations for K-half `kh` -> A operand + layer-1 sign bits
-      auto build_a1 = [&](int kh) {
+      // hand k-block kb of the A operand over to the MMA issuer
+      auto signal_kb = [&](int kb) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.a_ready[kb]);
+      };
+      // store 32 features (k-block kb, half h) of this row as bf16 hi [+ lo] into region `reg`
+      auto store_a = [&](uint32_t reg, int kb, const float (&v)[32]) {
+        uint32_t hi[16], lo[16];
+        split_pack<X3>(v, hi, lo);
+        const uint32_t col = reg * 256u + (uint32_t)(kb * 64 + h * 16);
+        tmem_st16(lane_addr + col, hi);
+        if (X3) tmem_st16(lane_addr + col + 32, lo);
+      };
+      // layer-1 activations for K-half `kh` -> A operand in region `reg` + layer-1 sign bits
+      auto build_a1 = [&](int kh, uint32_t reg) {
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col0 = kh * 256 + h * 128 + c * 32;
+        for (int kb = 0; kb < 4; ++kb) {
+          const int col0 = kh * 256 + kb * 64 + h * 32;
           float v[32];
           uint32_t bits = 0;
 #pragma unroll
@@ -344,69 +374,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             bits |= (a.x > 0.f ? 1u : 0u) << i | (a.y > 0.f ? 1u : 0u) << (i + 1) | (a.z > 0.f ? 1u : 0u) << (i + 2) |
                     (a.w > 0.f ? 1u : 0u) << (i + 3);
           }
-          S.mask[kh * 8 + h * 4 + c][row] = bits;
-          uint32_t hi[16], lo[16];
-          split_pack<X3>(v, hi, lo);
-          const uint32_t acol = (uint32_t)(h * 64 + c * 16);
-          tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
-          if (X3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+          S.mask[kh * 8 + kb * 2 + h][row] = bits;
+          store_a(reg, kb, v);
+          signal_kb(kb);
         }
       };
-      auto signal_a = [&]() {
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.a_ready);
-      };
 
-      build_a1(0);
-      signal_a();
+      build_a1(0, 0);
 
-      float dl0 = 0.f, dl1 = 0.f, dl2 = 0.f;
       for (int sg = 0; sg < P.n_seg; ++sg) {
         const Seg sgm = P.seg[sg];
+        const bool last_seg = sg == P.n_seg - 1;
+        const uint32_t dreg = cur ^ 1u;             // accumulator region of this segment
+        const uint32_t d_addr = lane_addr + dreg * 256u;
         mbar_wait(&S.d_ready, d_phase, P.err, 4);
         d_phase ^= 1;
         tc_fence_after();
-        const bool last_seg = sg == P.n_seg - 1;
 
         if (sgm.kind == K_MID) {
-          build_a1(1);
+          build_a1(1, cur);                         // second K-half of a1 replaces the first; accumulator stays
         } else if (sgm.kind == K_FWD || sgm.kind == K_BWD) {
-          // FWD: a = relu(D + b), record sign bits of layer `layer`.   BWD: d = D * 1[a_{layer} > 0].
-          const int mbase = sgm.layer == 0 ? 0 : l1_words + (sgm.layer - 1) * 8;   // mask row of trunk layer index
-          // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed
+          // FWD: a = relu(D + b), record sign bits of this layer.   BWD: d = D * 1[a_{layer} > 0].
+          const int mbase = sgm.layer == 0 ? 0 : l1_words + (sgm.layer - 1) * 8;
           uint32_t rr[2][32];
-          tmem_ld32_async(lane_addr + TMEM_D + (uint32_t)(h * 128), rr[0]);
+          tmem_ld32_async(d_addr + (uint32_t)(h * 32), rr[0]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            tmem_ld_wait32(rr[c & 1]);
-            if (c + 1 < 4) tmem_ld32_async(lane_addr + TMEM_D + (uint32_t)(h * 128 + (c + 1) * 32), rr[(c + 1) & 1]);
+          for (int kb = 0; kb < 4; ++kb) {
+            tmem_ld_wait32(rr[kb & 1]);
+            if (kb + 1 < 4) tmem_ld32_async(d_addr + (uint32_t)((kb + 1) * 64 + h * 32), rr[(kb + 1) & 1]);
+            pair_sync();                            // both halves of k-block kb are now in registers
             float v[32];
             if (sgm.kind == K_FWD) {
-              const float* b = &S.bias[sgm.layer - 1][h * 128 + c * 32];
+              const float* b = &S.bias[sgm.layer - 1][kb * 64 + h * 32];
               uint32_t bits = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                float z = __uint_as_float(rr[c & 1][i]) + b[i];
+                float z = __uint_as_float(rr[kb & 1][i]) + b[i];
                 bits |= (z > 0.f ? 1u : 0u) << i;
                 v[i] = fmaxf(z, 0.f);
               }
-              S.mask[mbase + h * 4 + c][row] = bits;
+              S.mask[mbase + kb * 2 + h][row] = bits;
             } else {
-              const uint32_t bits = S.mask[mbase + h * 4 + c][row];
+              const uint32_t bits = S.mask[mbase + kb * 2 + h][row];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? __uint_as_float(rr[c & 1][i]) : 0.f;
+              for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? __uint_as_float(rr[kb & 1][i]) : 0.f;
             }
-            uint32_t hi[16], lo[16];
-            split_pack<X3>(v, hi, lo);
-            const uint32_t acol = (uint32_t)(h * 64 + c * 16);
-            tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
-            if (X3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+            store_a(dreg, kb, v);                   // in place: the accumulator region becomes the next A operand
+            signal_kb(kb);
           }
+          cur ^= 1;
         } else if (sgm.kind == K_OUT) {
           uint32_t rr[8];
-          tmem_ld8(lane_addr + TMEM_D, rr);
+          tmem_ld8(d_addr, rr);
           const float l0 = __uint_as_float(rr[0]) + S.b_out[0], l1 = __uint_as_float(rr[1]) + S.b_out[1],
                       l2 = __uint_as_float(rr[2]) + S.b_out[2];
           if (h == 0 && live && P.logits) {
@@ -426,25 +445,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
               asm volatile("bar.sync 1, 256;" ::: "memory");
             }
           } else {
-            // seed of the backward pass: d8 = (dObj/dlogits . W_out) * 1[a_8 > 0]
-            dl0 = coef * (P.obj.c[0] + 2.f * P.obj.sq0 * l0); dl1 = coef * P.obj.c[1]; dl2 = coef * P.obj.c[2];
+            // seed of the backward pass: d8 = (dObj/dlogits . W_out) * 1[a_8 > 0], written over the logits' region
+            const float dl0 = coef * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = coef * P.obj.c[1], dl2 = coef * P.obj.c[2];
             const int mbase = l1_words + 6 * 8;
+            pair_sync();                            // the other half has read the logits too
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              const int col0 = h * 128 + c * 32;
-              const uint32_t bits = S.mask[mbase + h * 4 + c][row];
+            for (int kb = 0; kb < 4; ++kb) {
+              const int col0 = kb * 64 + h * 32;
+              const uint32_t bits = S.mask[mbase + kb * 2 + h][row];
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 float d = dl0 * S.w_out[0][col0 + i] + dl1 * S.w_out[1][col0 + i] + dl2 * S.w_out[2][col0 + i];
                 v[i] = (bits >> i) & 1u ? d : 0.f;
               }
-              uint32_t hi[16], lo[16];
-              split_pack<X3>(v, hi, lo);
-              const uint32_t acol = (uint32_t)(h * 64 + c * 16);
-              tmem_st16(lane_addr + TMEM_A_HI + acol, hi);
-              if (X3) tmem_st16(lane_addr + TMEM_A_LO + acol, lo);
+              store_a(dreg, kb, v);
+              signal_kb(kb);
             }
+            cur ^= 1;
           }
         } else {   // K_LAST: d1 = D * 1[a_1 > 0], summed over the rows of each pair present in the tile (K2)
           for (int64_t ps = p_first; ps <= p_last; ++ps) {
@@ -452,7 +470,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
               uint32_t rr[32];
-              tmem_ld32(lane_addr + TMEM_D + (uint32_t)(h * 128 + c * 32), rr);
+              tmem_ld32(d_addr + (uint32_t)(h * 128 + c * 32), rr);
               const uint32_t bits = mine ? S.mask[sgm.half * 8 + h * 4 + c][row] : 0u;
               float v[32];
 #pragma unroll
@@ -466,10 +484,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
           }
+          if (!last_seg) {                          // 3D: second N-half reuses the same A operand
+#pragma unroll 1
+            for (int kb = 0; kb < 4; ++kb) signal_kb(kb);
+          }
         }
-        if (!last_seg) signal_a();
       }
-      (void)dl0; (void)dl1; (void)dl2;
     }
   }
 
