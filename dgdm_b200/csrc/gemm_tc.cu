@@ -6,13 +6,13 @@
 // out of the zero-padded channels-last activation buffers through the same (sample, row, tap) mapping as the
 // CUDA-core GEMM (GemmArgs, common.cuh) -- no im2col.
 //
-// One persistent CTA per SM, 10 warps, 128 output rows per tile, all N (128 or 256) columns per tile:
-//   warps 4-7  A producers: each thread owns one row of the tile; per 64-wide k-block it loads 256 contiguous
-//              bytes of fp32 (one tap, 64 channels), splits to bf16 hi/lo and writes the 128-byte row into shared
+// One persistent CTA per SM, 14 warps, 128 output rows per tile, all N (128 or 256) columns per tile:
+//   warps 4-11 A producers: each thread owns half a row of the tile; per 64-wide k-block it loads 128 contiguous
+//              bytes of fp32 (one tap, 32 channels), splits to bf16 hi/lo and writes its half of the 128-byte row into shared
 //              memory in the canonical K-major SWIZZLE_128B layout (16-byte chunk j of row r at chunk j^(r&7)),
 //              then fence.proxy.async + mbarrier arrive.
-//   warp 8     W producer: cp.async.bulk (TMA unit) of the pre-packed, pre-swizzled weight tiles (gemm_tc_pack).
-//   warp 9     MMA issuer: tcgen05.mma.cta_group::1.kind::f16, A and B from shared memory, M=128 x N x K=16,
+//   warp 12    W producer: cp.async.bulk (TMA unit) of the pre-packed, pre-swizzled weight tiles (gemm_tc_pack).
+//   warp 13    MMA issuer: tcgen05.mma.cta_group::1.kind::f16, A and B from shared memory, M=128 x N x K=16,
 //              fp32 accumulators in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i overlaps
 //              the main loop of tile i+1.
 //   warps 0-3  epilogue: tcgen05.ld, + bias, activation, 128-bit stores through the C row mapping.
@@ -23,7 +23,7 @@
 namespace dgdm {
 namespace {
 
-constexpr int TM = 128, KB = 64, NTHR = 320;
+constexpr int TM = 128, KB = 64, NTHR = 448;   // 4 epilogue + 8 A-producer + W-producer + MMA warps
 constexpr int A_TILE = TM * 128;               // 16 KB: 128 rows x 128 B
 constexpr int SMEM_BUDGET = 200 * 1024;
 constexpr int MAX_STAGE = 4;
@@ -98,11 +98,11 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
   const uint32_t off_alo = A_TILE, off_whi = P.x3 ? 2 * A_TILE : A_TILE, off_wlo = off_whi + w_tile;
 
   if (tid == 0) {
-    for (int s = 0; s < P.n_stage; ++s) { bar_init(&S.full_a[s], 4); bar_init(&S.full_w[s], 1); bar_init(&S.empty[s], 1); }
+    for (int s = 0; s < P.n_stage; ++s) { bar_init(&S.full_a[s], 8); bar_init(&S.full_w[s], 1); bar_init(&S.empty[s], 1); }
     for (int i = 0; i < 2; ++i) { bar_init(&S.d_full[i], 1); bar_init(&S.d_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == 13) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(&S.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -112,9 +112,12 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
   const uint32_t tmem = S.tmem_base;
   const int my_tiles = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 12) {
     // ------------------------------- A producers -------------------------------
-    const int r = (warp - 4) * 32 + lane;          // row of the tile owned by this thread
+    // warp pair (p, p+4) shares 32 rows: each thread converts half a 64-wide k-block row (32 fp32 = 128 B)
+    const int pw = warp - 4;
+    const int r = (pw & 3) * 32 + lane;            // row of the tile owned by this thread
+    const int half = pw >> 2;                      // which 32-element half of the k-block row
     uint32_t stage = 0, phase = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t m = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TM + r;
@@ -122,15 +125,16 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
       const float* arow = g.A + (live ? (m / g.a_lr) * g.a_ss + (m % g.a_lr) * g.a_rs : 0);
       for (int kb = 0; kb < P.n_kb; ++kb) {
         const int k0 = kb * KB;
-        const float* src = arow + (int64_t)(k0 / g.a_ct) * g.a_ts + (k0 % g.a_ct);
-        float4 v[16];
+        const float* src = arow + (int64_t)(k0 / g.a_ct) * g.a_ts + (k0 % g.a_ct) + half * 32;
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = live ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) v[i] = live ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         bar_wait(&S.empty[stage], phase ^ 1, P.err, 11);
         uint8_t* st = ring + (size_t)stage * P.stage_bytes;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                // 16-byte chunk j = 8 bf16 = two float4
-          const float f[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w, v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+        for (int jj = 0; jj < 4; ++jj) {             // 16-byte chunk j = 8 bf16 = two float4
+          const int j = half * 4 + jj;
+          const float f[8] = {v[2 * jj].x, v[2 * jj].y, v[2 * jj].z, v[2 * jj].w, v[2 * jj + 1].x, v[2 * jj + 1].y, v[2 * jj + 1].z, v[2 * jj + 1].w};
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
         if (++stage == (uint32_t)P.n_stage) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ------------------------------- W producer -------------------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 13) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }

@@ -21,12 +21,16 @@ int gemm_tc(const GemmArgs& g, const void* wimg, int x3, int* err, cudaStream_t 
 namespace {
 
 constexpr int PADL = 2;          // zero rows before/after each sample
-constexpr int CHUNK = 4096;      // samples per pass (bounds workspace)
+constexpr int CHUNK = 16384;     // samples per pass (bounds workspace: 1.7 GB at P=14, 3.9 GB at P=42)
 constexpr int DSED = 32;
 
+// mish(x) = x tanh(softplus(x)); with e = exp(x): tanh(log(1+e)) = n / (n + 2), n = e (e + 2).
+// One exp and one division instead of exp + log1p + tanh; x > 20 returns x (torch's softplus threshold).
 __device__ __forceinline__ float mish(float x) {
-  float sp = x > 20.f ? x : log1pf(expf(x));   // softplus, torch threshold 20
-  return x * tanhf(sp);
+  if (x > 20.f) return x;
+  const float e = expf(x);
+  const float n = e * (e + 2.f);
+  return x * (n / (n + 2.f));
 }
 
 // cond = Linear(Mish(Linear(SinusoidalPosEmb(t))));  film[b] = Linear_b(Mish(cond)) for the 8 res blocks.
@@ -81,38 +85,76 @@ struct GnArgs {
   const float* in; float* out; const float* res; const float* gamma; const float* beta; const float* film;
   int64_t n; int L, C, ldi, ldo, ldr;
 };
+// One warp per (sample, group); the group's L x C/8 block is read ONCE with 128-bit loads and kept in
+// registers (MAXV float4 per lane) for the mean, the centred variance and the normalise/Mish/FiLM/residual pass.
+template <int MAXV>
 __global__ void __launch_bounds__(256) gn_mish_kernel(GnArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= a.n * 8) return;
   const int64_t b = wid >> 3;
   const int grp = (int)(wid & 7);
-  const int cg = a.C / 8, cnt = cg * a.L;
+  const int cg = a.C / 8, cg4 = cg / 4, cnt4 = cg4 * a.L, cnt = cg * a.L;
   const int rows = a.L + 2 * PADL;
   const float* ip = a.in + (b * rows + PADL) * a.ldi + grp * cg;
+  float4 x[MAXV];
   float s = 0.f;
-  for (int i = lane; i < cnt; i += 32) s += ip[(int64_t)(i / cg) * a.ldi + (i % cg)];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int j = lane + 32 * k;
+    x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < cnt4) {
+      x[k] = *reinterpret_cast<const float4*>(ip + (int64_t)(j / cg4) * a.ldi + (j % cg4) * 4);
+      s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)cnt;
   float v = 0.f;
-  for (int i = lane; i < cnt; i += 32) {
-    float d = ip[(int64_t)(i / cg) * a.ldi + (i % cg)] - mean;
-    v = fmaf(d, d, v);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    if (lane + 32 * k < cnt4) {
+      float d0 = x[k].x - mean, d1 = x[k].y - mean, d2 = x[k].z - mean, d3 = x[k].w - mean;
+      v = fmaf(d0, d0, v); v = fmaf(d1, d1, v); v = fmaf(d2, d2, v); v = fmaf(d3, d3, v);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const float rstd = rsqrtf(v / (float)cnt + 1e-5f);
   float* op = a.out + (b * rows + PADL) * a.ldo + grp * cg;
   const float* rp = a.res ? a.res + (b * rows + PADL) * a.ldr + grp * cg : nullptr;
-  for (int i = lane; i < cnt; i += 32) {
-    int l = i / cg, c = i % cg, ch = grp * cg + c;
-    float y = (ip[(int64_t)l * a.ldi + c] - mean) * rstd * a.gamma[ch] + a.beta[ch];
-    y = mish(y);
-    if (a.film) y = a.film[ch] * y + a.film[a.C + ch];
-    if (rp) y += rp[(int64_t)l * a.ldr + c];
-    op[(int64_t)l * a.ldo + c] = y;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int j = lane + 32 * k;
+    if (j >= cnt4) continue;
+    const int l = j / cg4, c = (j % cg4) * 4, ch = grp * cg + c;
+    const float4 gm = *reinterpret_cast<const float4*>(a.gamma + ch), bt = *reinterpret_cast<const float4*>(a.beta + ch);
+    float4 y;
+    y.x = mish((x[k].x - mean) * rstd * gm.x + bt.x);
+    y.y = mish((x[k].y - mean) * rstd * gm.y + bt.y);
+    y.z = mish((x[k].z - mean) * rstd * gm.z + bt.z);
+    y.w = mish((x[k].w - mean) * rstd * gm.w + bt.w);
+    if (a.film) {
+      const float4 sc = *reinterpret_cast<const float4*>(a.film + ch), sh = *reinterpret_cast<const float4*>(a.film + a.C + ch);
+      y.x = sc.x * y.x + sh.x; y.y = sc.y * y.y + sh.y; y.z = sc.z * y.z + sh.z; y.w = sc.w * y.w + sh.w;
+    }
+    if (rp) {
+      const float4 r = *reinterpret_cast<const float4*>(rp + (int64_t)l * a.ldr + c);
+      y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+    }
+    *reinterpret_cast<float4*>(op + (int64_t)l * a.ldo + c) = y;
   }
+}
+
+int launch_gn(const GnArgs& a, cudaStream_t s) {
+  const int cnt4 = (a.C / 8 / 4) * a.L;
+  const unsigned blocks = (unsigned)((a.n * 8 * 32 + 255) / 256);
+  if (cnt4 <= 64) gn_mish_kernel<2><<<blocks, 256, 0, s>>>(a);
+  else if (cnt4 <= 192) gn_mish_kernel<6><<<blocks, 256, 0, s>>>(a);
+  else { set_error("GroupNorm block of %d float4 is larger than supported (P <= 48)", cnt4); return DGDM_EUNSUPPORTED; }
+  DGDM_LAUNCH_CHECK();
+  return DGDM_OK;
 }
 
 // eps[b,l] = sum_c h[b][l][c] * w[c] + bias      (final_conv.1, Conv1d(128,1,1))
@@ -187,7 +229,8 @@ struct Bufs {
 
 size_t bufs_floats(int64_t n, int L) {
   const int L2 = L / 2;
-  return (size_t)n * (L + 4) * (1 + 3 * 128) + (size_t)n * (L2 + 4) * (3 * 128 + 3 * 256 + 512);
+  const size_t x0 = ((size_t)n * (L + 4) + 63) / 64 * 64;     // keeps every later buffer 256-byte aligned
+  return x0 + (size_t)n * (L + 4) * (3 * 128) + (size_t)n * (L2 + 4) * (3 * 128 + 3 * 256 + 512);
 }
 
 // One ConditionalResidualBlock1D (diffusion_utils.py:100-120).
@@ -203,8 +246,7 @@ int res_block(const dgdm_unet_resblock& w, const float* film, const float* in, i
   DGDM_TRY(conv_gemm(in, ldi, rows, ci, 5, 1, 0, w.conv0_w, w.conv0_b, t0, co, rows, co, 1, 0, n, L, s,
                      pl.conv0[bi] == (size_t)-1 ? nullptr : tc, pl.conv0[bi]));
   GnArgs g0{t0, t0, nullptr, w.gn0_w, w.gn0_b, film, n, L, co, co, co, 0};
-  gn_mish_kernel<<<nblk(n * 8 * 32, 256), 256, 0, s>>>(g0);
-  DGDM_LAUNCH_CHECK();
+  DGDM_TRY(launch_gn(g0, s));
   // block 1: conv5 -> GN -> Mish, + residual
   DGDM_TRY(conv_gemm(t0, co, rows, co, 5, 1, 0, w.conv1_w, w.conv1_b, t1, co, rows, co, 1, 0, n, L, s, tc, pl.conv1[bi]));
   const float* res = in;
@@ -216,8 +258,7 @@ int res_block(const dgdm_unet_resblock& w, const float* film, const float* in, i
     ldr = co;
   }
   GnArgs g1{t1, out, res, w.gn1_w, w.gn1_b, nullptr, n, L, co, co, ldo, ldr};
-  gn_mish_kernel<<<nblk(n * 8 * 32, 256), 256, 0, s>>>(g1);
-  DGDM_LAUNCH_CHECK();
+  DGDM_TRY(launch_gn(g1, s));
   return DGDM_OK;
 }
 
@@ -262,7 +303,7 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
   using namespace dgdm;
   DGDM_CHECK_ARG(w && x && eps && workspace, "dgdm_unet1d_forward: null pointer");
   DGDM_CHECK_ARG(n >= 1, "dgdm_unet1d_forward: n=%d", n);
-  DGDM_CHECK_ARG(P >= 2 && P % 2 == 0, "dgdm_unet1d_forward: P=%d must be even (one stride-2 level)", P);
+  DGDM_CHECK_ARG(P >= 2 && P % 2 == 0 && P <= 48, "dgdm_unet1d_forward: P=%d must be even (one stride-2 level) and <= 48", P);
   static const int kCin[8] = {1, 128, 128, 256, 256, 256, 512, 128};
   static const int kCout[8] = {128, 128, 256, 256, 256, 256, 128, 128};
   for (int b = 0; b < 8; ++b)
@@ -280,7 +321,7 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
   if (!ar.ok) { set_error("dgdm_unet1d_forward: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
   {
     float* p = big;
-    B.x0 = p; p += (size_t)nc * R;
+    B.x0 = p; p += ((size_t)nc * R + 63) / 64 * 64;
     B.a = p; p += (size_t)nc * R * 128; B.b = p; p += (size_t)nc * R * 128; B.c = p; p += (size_t)nc * R * 128;
     B.p = p; p += (size_t)nc * R2 * 128; B.ta = p; p += (size_t)nc * R2 * 128; B.tb = p; p += (size_t)nc * R2 * 128;
     B.q = p; p += (size_t)nc * R2 * 256; B.r = p; p += (size_t)nc * R2 * 256; B.u = p; p += (size_t)nc * R2 * 256;
@@ -331,8 +372,7 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
     // final: Conv1dBlock(128,128,5) then Conv1d(128,1,1)
     DGDM_TRY(conv_gemm(B.a, 128, R, 128, 5, 1, 0, w->fin_w, w->fin_b, B.b, 128, R, 128, 1, 0, m, L, s, tc, pl.fin));
     GnArgs gf{B.b, B.b, nullptr, w->fin_gn_w, w->fin_gn_b, nullptr, m, L, 128, 128, 128, 0};
-    gn_mish_kernel<<<nblk(m * 8 * 32, 256), 256, 0, s>>>(gf);
-    DGDM_LAUNCH_CHECK();
+    DGDM_TRY(launch_gn(gf, s));
     out_proj_kernel<<<nblk(m * L * 32, 256), 256, 0, s>>>(eps + n0 * L, B.b, w->out_w, w->out_b, m, L, 128);
     DGDM_LAUNCH_CHECK();
   }
