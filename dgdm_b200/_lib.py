@@ -68,6 +68,9 @@ EXPORTS = {
                                     C.c_int32, fp]),
     "dgdm_dyn_score": (C.c_int, [C.POINTER(DynWeights), fp, C.c_int32, fp, C.c_int32, C.c_int32, fp, C.c_float,
                                  C.POINTER(PoseGrid), C.POINTER(Objective), fp, fp, fp, C.c_size_t, C.c_int32, fp]),
+    "dgdm_dyn_rows_workspace_bytes": (C.c_size_t, [C.POINTER(DynWeights), C.c_int64, C.c_int32]),
+    "dgdm_dyn_forward_rows": (C.c_int, [C.POINTER(DynWeights), fp, fp, fp, fp, fp, C.c_int64, C.POINTER(Objective), fp, fp,
+                                        fp, C.c_size_t, C.c_int32, fp]),
     "dgdm_unet1d_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "dgdm_unet1d_forward": (C.c_int, [C.POINTER(UnetWeights), fp, C.c_int32, C.c_int32, C.c_int32, fp, fp,
                                       C.c_size_t, C.c_int32, fp]),

@@ -77,6 +77,44 @@ __global__ void time_embed_kernel(float* __restrict__ out, float t, int dim) {
   out[half + i] = sinf(a);
 }
 
+// explicit rows: pose[r, 0:27] from (ori[r], pos[r,0:2]); same layout as pose_embed_kernel
+__global__ void pose_embed_rows_kernel(float* __restrict__ pose, const float* __restrict__ ori, const float* __restrict__ pos, int64_t n) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float o = ori[r], px = pos[2 * r], py = pos[2 * r + 1];
+  float* out = pose + r * 27;
+  out[0] = o;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { float f = (float)(1 << k); out[1 + 2 * k] = sinf(o * f); out[2 + 2 * k] = cosf(o * f); }
+  out[9] = px; out[10] = py;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float f = (float)(1 << k);
+    out[11 + 4 * k] = sinf(px * f); out[12 + 4 * k] = sinf(py * f);
+    out[13 + 4 * k] = cosf(px * f); out[14 + 4 * k] = cosf(py * f);
+  }
+}
+// explicit rows: temb[r, 0:dim] = [cos(t_r f_i) | sin(t_r f_i)]
+__global__ void time_embed_rows_kernel(float* __restrict__ out, const float* __restrict__ t, int64_t n, int dim) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= n * half) return;
+  const int64_t r = idx / half; const int i = (int)(idx % half);
+  const float a = t[r] * expf(-9.210340371976184f * (float)i / (float)half);
+  out[r * dim + i] = cosf(a);
+  out[r * dim + half + i] = sinf(a);
+}
+// base[r,:] = ((o[r,:] + u[r,:]) + v[r,:]) + tt[r,:]
+__global__ void sum4_kernel(float* __restrict__ base, const float* __restrict__ o, const float* __restrict__ u,
+                            const float* __restrict__ v, const float* __restrict__ tt, int64_t n4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<const float4*>(o)[i], b = reinterpret_cast<const float4*>(u)[i];
+  float4 c = reinterpret_cast<const float4*>(v)[i], d = reinterpret_cast<const float4*>(tt)[i];
+  reinterpret_cast<float4*>(base)[i] = make_float4(((a.x + b.x) + c.x) + d.x, ((a.y + b.y) + c.y) + d.y,
+                                                   ((a.z + b.z) + c.z) + d.z, ((a.w + b.w) + c.w) + d.w);
+}
+
 // a1[r,:] = relu(Cst[obj(p)] + U[design(p)] + V[g]),  r = p*G + g, rows [r0, r0+rows)
 __global__ void build_a1_kernel(float* __restrict__ a1, const float* __restrict__ U, const float* __restrict__ Cst,
                                 const float* __restrict__ V, int64_t r0, int64_t rows, int G, int H1, int opd,
@@ -347,6 +385,99 @@ int trunk_dispatch(const dgdm_dyn_weights* w, const Hoist& h, int nd, int n_obj,
 
 }  // namespace
 }  // namespace dgdm
+
+extern "C" size_t dgdm_dyn_rows_workspace_bytes(const dgdm_dyn_weights* w, int64_t n_rows, int32_t precision) {
+  using namespace dgdm;
+  if (!w || n_rows < 1) return 0;
+  auto a = [](size_t n) { return align_up(n * sizeof(float), 256); };
+  const int H1 = w->H1;
+  size_t b = a(n_rows * 256) * 8 + a((size_t)n_rows * H1) * 7 + a(n_rows * 27) + a(2 * (size_t)H1) + a(n_rows);
+  if (precision == DGDM_PREC_FP32_SIMT) b += simt_bytes(H1, n_rows);
+  else b += align_up(tc_trunk_workspace_bytes(H1, n_rows, 1), 256);
+  return b + 4096;
+}
+
+extern "C" int dgdm_dyn_forward_rows(const dgdm_dyn_weights* w, const float* x, const float* ori, const float* pos,
+                                     const float* t_frac, const float* objects, int64_t n_rows,
+                                     const dgdm_objective* objective, float* logits, float* grad_x, void* workspace,
+                                     size_t workspace_bytes, int32_t precision, void* stream) {
+  using namespace dgdm;
+  DGDM_CHECK_ARG(w && x && ori && pos && t_frac && objects && workspace, "dgdm_dyn_forward_rows: null pointer");
+  DGDM_CHECK_ARG(logits || grad_x, "dgdm_dyn_forward_rows: nothing to compute (logits and grad_x both NULL)");
+  DGDM_CHECK_ARG(!grad_x || objective, "dgdm_dyn_forward_rows: grad_x needs an objective");
+  DGDM_CHECK_ARG(n_rows >= 1 && n_rows < (1ll << 31), "dgdm_dyn_forward_rows: n_rows out of range");
+  DGDM_CHECK_ARG(w->H1 == 256 || w->H1 == 512, "dgdm_dyn_forward_rows: H1=%d unsupported", w->H1);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H1 = w->H1, P = w->P;
+  const int64_t n = n_rows;
+  Arena ar(workspace, workspace_bytes);
+  Hoist h{};
+  h.G = 1; h.n_pairs = n;
+  h.h0 = ar.take<float>(n * 256);
+  h.e = ar.take<float>(n * 256);
+  float* temb = ar.take<float>(n * 256);
+  float* th = ar.take<float>(n * 256);
+  float* te = ar.take<float>(n * 256);
+  h.oh = ar.take<float>(n * 256);
+  h.oc = ar.take<float>(n * 256);
+  h.de = ar.take<float>(n * 256);
+  h.dh0 = h.e;                                   // e is dead once U is formed
+  float* Ur = ar.take<float>((size_t)n * H1);
+  float* Vr = ar.take<float>((size_t)n * H1);
+  float* Tr = ar.take<float>((size_t)n * H1);
+  float* Or = ar.take<float>((size_t)n * H1);
+  h.U = ar.take<float>((size_t)n * H1);          // base = Or + Ur + Vr + Tr
+  h.dUp = ar.take<float>((size_t)n * H1);
+  h.dU = ar.take<float>((size_t)n * H1);
+  h.pose = ar.take<float>(n * 27);
+  float* zeros = ar.take<float>(2 * (size_t)H1);
+  h.score_sum = ar.take<float>(n);
+  if (!ar.ok) { set_error("dgdm_dyn_forward_rows: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
+  h.Cst = zeros; h.V = zeros + H1;
+  DGDM_CUDA(cudaMemsetAsync(zeros, 0, 2 * (size_t)H1 * sizeof(float), s));
+  // every encoder at row scale -- this is the un-hoistable "paired" mode of the forward signature
+  DGDM_TRY(gemm_f32(gemm_plain(x, P, w->ge_w0, w->ge_b0, h.h0, 256, n, 256, P, ACT_RELU), s));
+  DGDM_TRY(gemm_f32(gemm_plain(h.h0, 256, w->ge_w1, w->ge_b1, h.e, 256, n, 256, 256, ACT_NONE), s));
+  DGDM_TRY(gemm_f32(gemm_plain(h.e, 256, w->w1_ctrl, nullptr, Ur, H1, n, H1, 256, ACT_NONE), s));
+  pose_embed_rows_kernel<<<blocks_for(n, 128), 128, 0, s>>>(h.pose, ori, pos, n);
+  DGDM_LAUNCH_CHECK();
+  DGDM_TRY(gemm_f32(gemm_plain(h.pose, 27, w->w1_pose, nullptr, Vr, H1, n, H1, 27, ACT_NONE), s));
+  const float* tep;
+  if (w->is_3d) {
+    time_embed_rows_kernel<<<blocks_for(n * 128, 256), 256, 0, s>>>(temb, t_frac, n, 256);
+    DGDM_LAUNCH_CHECK();
+    tep = temb;
+  } else {
+    time_embed_rows_kernel<<<blocks_for(n * 64, 256), 256, 0, s>>>(temb, t_frac, n, 128);
+    DGDM_LAUNCH_CHECK();
+    DGDM_TRY(gemm_f32(gemm_plain(temb, 128, w->te_w0, w->te_b0, th, 256, n, 256, 128, ACT_SILU), s));
+    DGDM_TRY(gemm_f32(gemm_plain(th, 256, w->te_w1, w->te_b1, te, 256, n, 256, 256, ACT_NONE), s));
+    tep = te;
+  }
+  DGDM_TRY(gemm_f32(gemm_plain(tep, 256, w->w1_time, w->b1, Tr, H1, n, H1, 256, ACT_NONE), s));
+  const float* oc = objects;
+  if (!w->is_3d) {
+    DGDM_TRY(gemm_f32(gemm_plain(objects, w->obj_dim, w->oe_w0, w->oe_b0, h.oh, 256, n, 256, w->obj_dim, ACT_RELU), s));
+    DGDM_TRY(gemm_f32(gemm_plain(h.oh, 256, w->oe_w1, w->oe_b1, h.oc, 256, n, 256, 256, ACT_NONE), s));
+    oc = h.oc;
+  }
+  DGDM_TRY(gemm_f32(gemm_plain(oc, 256, w->w1_obj, nullptr, Or, H1, n, H1, 256, ACT_NONE), s));
+  sum4_kernel<<<blocks_for(n * H1 / 4, 256), 256, 0, s>>>(h.U, Or, Ur, Vr, Tr, n * H1 / 4);
+  DGDM_LAUNCH_CHECK();
+  dgdm_objective dummy{{0.f, 0.f, 0.f}, 0.f, nullptr};
+  const dgdm_objective* ob = objective ? objective : &dummy;
+  if (!grad_x) {
+    DGDM_TRY(trunk_dispatch(w, h, (int)n, 1, 1, nullptr, ob, false, logits, ar, precision, s));
+    return DGDM_OK;
+  }
+  DGDM_TRY(trunk_dispatch(w, h, (int)n, 1, 1, nullptr, ob, true, logits, ar, precision, s));
+  DGDM_TRY(gemm_f32(gemm_plain(h.dUp, H1, w->w1_ctrl_t, nullptr, h.de, 256, n, 256, H1, ACT_NONE), s));
+  GemmArgs g = gemm_plain(h.de, 256, w->ge_w1_t, nullptr, h.dh0, 256, n, 256, 256, ACT_NONE);
+  g.mask = h.h0;
+  DGDM_TRY(gemm_f32(g, s));
+  DGDM_TRY(gemm_f32(gemm_plain(h.dh0, 256, w->ge_w0_t, nullptr, grad_x, P, n, P, 256, ACT_NONE), s));
+  return DGDM_OK;
+}
 
 extern "C" size_t dgdm_dyn_guidance_workspace_bytes(const dgdm_dyn_weights* w, int32_t n_designs, int32_t n_obj,
                                                     int32_t objs_per_design, const dgdm_pose_grid* grid,

@@ -208,8 +208,8 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 struct Smem {
   uint64_t full[NSTAGE], empty[NSTAGE], a_ready[4], d_ready;
   uint32_t tmem_base, pad_;
-  float bias[7][256];
-  float w_out[3][256];
+  alignas(16) float bias[7][256];
+  alignas(16) float w_out[3][256];
   float b_out[4];
   float red[4][256];            // per lane-quadrant partial column sums
   float red_s[4];
@@ -405,13 +405,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             pair_sync();                            // both halves of k-block kb are now in registers
             float v[32];
             if (sgm.kind == K_FWD) {
-              const float* b = &S.bias[sgm.layer - 1][kb * 64 + h * 32];
+              const float4* b4 = reinterpret_cast<const float4*>(&S.bias[sgm.layer - 1][kb * 64 + h * 32]);
               uint32_t bits = 0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float z = __uint_as_float(rr[kb & 1][i]) + b[i];
-                bits |= (z > 0.f ? 1u : 0u) << i;
-                v[i] = fmaxf(z, 0.f);
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 bb = b4[i4];               // 128-bit broadcast load: 8 instead of 32 LSU ops
+                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int i = i4 * 4 + e;
+                  float z = __uint_as_float(rr[kb & 1][i]) + bv[e];
+                  bits |= (z > 0.f ? 1u : 0u) << i;
+                  v[i] = fmaxf(z, 0.f);
+                }
               }
               S.mask[mbase + kb * 2 + h][row] = bits;
             } else {
@@ -435,6 +441,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           if (!P.backward) {
             // forward only: per-pair sums of the objective over this tile's rows -> score_part[p + tile]
             const float val = live ? coef * (P.obj.c[0] * l0 + P.obj.c[1] * l1 + P.obj.c[2] * l2 + P.obj.sq0 * l0 * l0) : 0.f;
+            if (P.G == 1) {                         // explicit-row mode: one row per pair, nothing to reduce
+              if (h == 0 && live) P.score_part[pr + tile] = val;
+            } else
             for (int64_t ps = p_first; ps <= p_last; ++ps) {
               float s = (pr == ps) ? val : 0.f;
 #pragma unroll
@@ -454,10 +463,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
               const int col0 = kb * 64 + h * 32;
               const uint32_t bits = S.mask[mbase + kb * 2 + h][row];
               float v[32];
+              const float4* w0 = reinterpret_cast<const float4*>(&S.w_out[0][col0]);
+              const float4* w1 = reinterpret_cast<const float4*>(&S.w_out[1][col0]);
+              const float4* w2 = reinterpret_cast<const float4*>(&S.w_out[2][col0]);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float d = dl0 * S.w_out[0][col0 + i] + dl1 * S.w_out[1][col0 + i] + dl2 * S.w_out[2][col0 + i];
-                v[i] = (bits >> i) & 1u ? d : 0.f;
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 a0 = w0[i4], a1 = w1[i4], a2 = w2[i4];
+                const float d[4] = {dl0 * a0.x + dl1 * a1.x + dl2 * a2.x, dl0 * a0.y + dl1 * a1.y + dl2 * a2.y,
+                                    dl0 * a0.z + dl1 * a1.z + dl2 * a2.z, dl0 * a0.w + dl1 * a1.w + dl2 * a2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[i4 * 4 + e] = (bits >> (i4 * 4 + e)) & 1u ? d[e] : 0.f;
               }
               store_a(dreg, kb, v);
               signal_kb(kb);
@@ -465,6 +480,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             cur ^= 1;
           }
         } else {   // K_LAST: d1 = D * 1[a_1 > 0], summed over the rows of each pair present in the tile (K2)
+          if (P.G == 1) {                           // explicit-row mode: the row IS the pair; store it directly
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t rr[32];
+              tmem_ld32(d_addr + (uint32_t)(h * 128 + c * 32), rr);
+              if (live) {
+                const uint32_t bits = S.mask[sgm.half * 8 + h * 4 + c][row];
+                float4* o = reinterpret_cast<float4*>(P.part + (pr + tile) * P.H1 + sgm.half * 256 + h * 128 + c * 32);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  o[i / 4] = make_float4((bits >> i) & 1u ? __uint_as_float(rr[i]) : 0.f, (bits >> (i + 1)) & 1u ? __uint_as_float(rr[i + 1]) : 0.f,
+                                         (bits >> (i + 2)) & 1u ? __uint_as_float(rr[i + 2]) : 0.f, (bits >> (i + 3)) & 1u ? __uint_as_float(rr[i + 3]) : 0.f);
+              }
+            }
+          } else
           for (int64_t ps = p_first; ps <= p_last; ++ps) {
             const bool mine = pr == ps;
 #pragma unroll 1

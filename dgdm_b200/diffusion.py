@@ -290,6 +290,46 @@ class Diffusion:
                 ws.numel(), self.precision, _lib.stream_ptr()), "dgdm_dyn_score")
         return (scores, logits) if want_logits else scores
 
+    def classifier_model(self, pts: torch.Tensor, ori: torch.Tensor, pos: torch.Tensor, timesteps: torch.Tensor,
+                         object_vertices: torch.Tensor = None, *, object_codes: Optional[torch.Tensor] = None,
+                         fps_starts: Optional[torch.Tensor] = None, opt_obj: Optional[str] = None,
+                         return_grad: bool = False):
+        """The dynamics network called on explicit rows, with the reference's own signature
+        (``ProfileForward2DModel.forward`` profile_forward_2d.py:137-156 / ``ProfileForward3DModel.forward``
+        profile_forward_3d.py:67-86; call sites diffusion.py:487,496,500,516):
+        pts (N,P) [3D: (N,3,P), only row 1 is read], ori (N,1), pos (N,2), timesteps (N,) float in [0,1),
+        object_vertices 2D (N,2V) / 3D (N,3,512)  ->  logits (N,3).
+        3D per-row clouds run PointNet++ per row (as the reference does); pass ``object_codes`` (N,256) to reuse
+        codes.  ``return_grad`` also returns d/dpts of sum_r objective(logits_r) for ``opt_obj``."""
+        f = lambda a: a.to(device=self.device, dtype=torch.float32).contiguous()
+        if self.mode == "point_3d":
+            x = f(pts[:, 1, :]) if pts.dim() == 3 else f(pts)
+            if object_codes is None:
+                if object_vertices is None:
+                    raise ValueError("object vertices not provided")
+                clouds = object_vertices.to(self.device).permute(0, 2, 1)        # (N,512,3)
+                object_codes = self.encode_objects(clouds, fps_starts)
+            objs = f(object_codes)
+        else:
+            x = f(pts)
+            if object_vertices is None:
+                raise ValueError("object vertices not provided")
+            objs = f(object_vertices.reshape(object_vertices.shape[0], -1))
+        n = x.shape[0]
+        o, p, t = f(ori.reshape(n)), f(pos.reshape(n, 2)), f(timesteps.reshape(n))
+        logits = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        grad = torch.empty_like(x) if return_grad else None
+        obj = _objective_struct(opt_obj) if opt_obj is not None else None
+        if return_grad and obj is None:
+            raise ValueError("return_grad needs opt_obj")
+        ws = self._workspace("dyn", self.lib.dgdm_dyn_rows_workspace_bytes(C.byref(self.dyn.struct), n, self.precision))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dgdm_dyn_forward_rows(
+                C.byref(self.dyn.struct), x.data_ptr(), o.data_ptr(), p.data_ptr(), t.data_ptr(), objs.data_ptr(), n,
+                C.byref(obj) if obj is not None else None, logits.data_ptr(), _lib.ptr(grad), ws.data_ptr(), ws.numel(),
+                self.precision, _lib.stream_ptr()), "dgdm_dyn_forward_rows")
+        return (logits, grad) if return_grad else logits
+
     def best_of_n(self, scores: torch.Tensor, k: int = 1):
         """scores (n_obj, n_cand) -> (idx int64 (n_obj,k), best (n_obj,k)); ties to the lowest index (np.argmax)."""
         s = scores.to(device=self.device, dtype=torch.float32).contiguous()

@@ -150,6 +150,19 @@ int dgdm_dyn_score(const dgdm_dyn_weights* w, const float* x, int32_t n_designs,
                    const dgdm_objective* objective, float* scores, float* logits, void* workspace,
                    size_t workspace_bytes, int32_t precision, void* stream);
 
+/* Explicit rows -- the forward signature of the dynamics networks themselves,
+ *   classifier_model(pts, ori, pos, t_float, object_vertices) -> (N,3)
+ * (ProfileForward2DModel.forward, dynamics/profile_forward_2d.py:137-156; call sites generator/diffusion.py:487,496,
+ * 500,516), where every row brings its own finger, pose, time and object, so nothing can be hoisted (BASELINE.json
+ * configs[3], the "paired" throughput sweep).  x [N,P]; ori [N]; pos [N,2]; t_frac [N]; objects 2D [N,obj_dim] /
+ * 3D [N,256] PointNet++ codes.  logits [N,3] (out, may be NULL).  If grad_x != NULL it receives
+ * d/dx_r objective(logits_r), [N,P] (forward + input-gradient). */
+size_t dgdm_dyn_rows_workspace_bytes(const dgdm_dyn_weights* w, int64_t n_rows, int32_t precision);
+int dgdm_dyn_forward_rows(const dgdm_dyn_weights* w, const float* x, const float* ori, const float* pos,
+                          const float* t_frac, const float* objects, int64_t n_rows, const dgdm_objective* objective,
+                          float* logits, float* grad_x, void* workspace, size_t workspace_bytes, int32_t precision,
+                          void* stream);
+
 /* Optional CUDA-event timing of the dominant kernel (the fused tensor-core trunk), used by bench.py for the
  * roofline line.  enable != 0 resets the counters and makes every subsequent launch of that kernel record an
  * event pair on its own stream; read() synchronises those events and returns the summed device time, the number

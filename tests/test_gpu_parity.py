@@ -273,6 +273,49 @@ def test_cond_fn_2d_vs_oracle_ragged(precision, B, grid, npos, n_obj):
         grad_close(gm.reshape(B, 14, 1), want.mean(0), tol_for(precision, grid * npos ** 2), name + " multi")
 
 
+# ---------------------------------------------------------------------------------------------- explicit rows (C4)
+@pytest.mark.parametrize("precision", ALL_MODES)
+def test_classifier_model_rows_golden(g2, g3, precision):
+    """The dynamics networks on explicit rows (their own forward signature), every row with its own finger, pose,
+    time and object: the reference's outputs from the golden fixtures."""
+    tol = {"fp32_simt": 1e-5, "fp32": 1e-4, "bf16": 2e-2}[precision]
+    dm = make2d(precision, torch.from_numpy(g2["objects"]), 2, 1)
+    lg = dm.classifier_model(*(torch.from_numpy(g2[k]) for k in ("fwd_ctrl", "fwd_ori", "fwd_pos", "fwd_t")),
+                             object_vertices=torch.from_numpy(g2["fwd_obj"]))
+    assert lg.shape == (37, 3) and rel(lg, g2["fwd_logits"]) < tol, rel(lg, g2["fwd_logits"])
+    dm3 = make3d(precision, torch.from_numpy(g3["objects"]), torch.from_numpy(g3["fps_starts"]), 3, 2)
+    n = g3["fwd_ctrl"].shape[0]
+    clouds = torch.from_numpy(g3["objects"][1]).t()[None].repeat(n, 1, 1)          # (N,3,512) per-row clouds
+    lg3 = dm3.classifier_model(torch.from_numpy(g3["fwd_ctrl"]), torch.from_numpy(g3["fwd_ori"]), torch.from_numpy(g3["fwd_pos"]),
+                               torch.from_numpy(g3["fwd_t"]), object_vertices=clouds,
+                               fps_starts=torch.from_numpy(g3["fps_starts"][1:2]).repeat(n, 1))
+    assert rel(lg3, g3["fwd_logits_o1"]) < tol, rel(lg3, g3["fwd_logits_o1"])
+
+
+@pytest.mark.parametrize("precision", ALL_MODES)
+@pytest.mark.parametrize("n", [1, 200, 1025])
+def test_classifier_model_rows_grad_vs_oracle(n, precision):
+    """Paired mode forward + input gradient (BASELINE.json configs[3] shape) against autograd on the oracle."""
+    rs = np.random.RandomState(n)
+    objs = syn.objects_2d(5, seed_base=1700)
+    x = torch.from_numpy(rs.randn(n, 14).astype(np.float32))
+    ori = torch.from_numpy(rs.uniform(-1, 1, (n, 1)).astype(np.float32))
+    pos = torch.from_numpy(rs.uniform(-1, 1, (n, 2)).astype(np.float32))
+    t = torch.from_numpy((rs.randint(0, 15, n) / 15.0).astype(np.float32))
+    ov = objs[rs.randint(0, 5, n)].reshape(n, -1)
+    sd = orc.strip_prefix(syn.dynamics2d_state_dict(0))
+    xr = x.clone().requires_grad_(True)
+    want_lg = orc.dynamics2d_forward(sd, xr, ori, pos, t, ov)
+    want_g = torch.autograd.grad(orc.deltas_to_objective(want_lg, "rotate").sum(), xr)[0]
+    dm = make2d(precision, objs, 2, 1)
+    lg, g = dm.classifier_model(x, ori, pos, t, object_vertices=ov, opt_obj="rotate", return_grad=True)
+    tol = {"fp32_simt": 1e-4, "fp32": 1e-3, "bf16": 2e-2}[precision]
+    assert rel(lg, want_lg) < tol
+    # every row is its own "candidate" with a single pose row: per-row kink flips do not average out, so compare
+    # in aggregate with the outlier rule and the single-row (G = 1) scaling
+    grad_close(g.reshape(n, 14, 1), want_g.reshape(n, 14, 1), tol_for(precision, 1) if precision != "fp32_simt" else 1e-4, "rows")
+
+
 # ---------------------------------------------------------------------------------------------- K5 + 3D
 def test_pointnet2_golden(g3):
     dm = make3d("fp32_simt", torch.from_numpy(g3["objects"]), torch.from_numpy(g3["fps_starts"]), int(g3["grid_size"]), int(g3["num_pos"]))
