@@ -419,6 +419,38 @@ class Diffusion:
             x = self.noise_scheduler.guided_step(eps, t, x, None, 0.0, out=x)
         return x.reshape(noise.shape)
 
+    def denoise_from_data(self, tensor_data: torch.Tensor, seed: Optional[int] = None) -> Dict[str, float]:
+        """The denoise-from-data validation metrics of ``validation_step`` (diffusion.py:179-201, 230-244): noise the
+        data at t = num_inference_steps with RandomState(seed) noise, run the unguided schedule, report
+        'val/noise pred loss', 'val/denoise loss', 'val/accuracy'."""
+        B = tensor_data.shape[0]
+        data = self._check_noise(tensor_data, B)
+        rs = np.random.RandomState(self.seed if seed is None else seed)
+        noise = torch.from_numpy(rs.randn(B, self.num_points, 1)).float().to(self.device).reshape(B, -1).contiguous()
+        a = self.noise_scheduler.alphas_cumprod[self.num_inference_steps]
+        # add_noise: sqrt(a) x0 + sqrt(1-a) eps  ==  K4 with an identity x0 stage (sqrt_1m_at = 0, sqrt_at = 1, no clip)
+        sample = torch.empty_like(data)
+        _lib.check(self.lib.dgdm_ddim_guided_update(sample.data_ptr(), data.data_ptr(), noise.data_ptr(), None, data.numel(),
+                                                    0.0, 1.0, float(a ** 0.5), float((1 - a) ** 0.5), 0.0, 0,
+                                                    _lib.stream_ptr()), "dgdm_ddim_guided_update")
+        npl = 0.0
+        for t in self.noise_scheduler.timesteps.tolist():
+            eps = self.noise_pred_net(sample, t)
+            npl += float(torch.mean((eps - noise) ** 2))
+            sample = self.noise_scheduler.guided_step(eps, t, sample, None, 0.0)
+        return {"val/noise pred loss": npl / self.num_inference_steps,
+                "val/denoise loss": float(torch.mean((sample - data) ** 2)),
+                "val/accuracy": float(torch.mean((torch.abs(sample - data) < 0.01).float()))}
+
+    def predicted_objectives(self, designs: torch.Tensor, object_vertices: torch.Tensor, opt_obj: str,
+                             ori_range=(-1.0, 1.0)):
+        """Prediction-side stand-in for the reference's MuJoCo tables (diffusion.py:583-598): per-candidate objective
+        dicts from the profile pass and the best candidate per metric key (dgdm_b200.metrics)."""
+        from . import metrics as M
+        lg = self.profile_logits(designs, object_vertices, ori_range).cpu().numpy()
+        objs = M.predicted_objectives(lg, opt_obj, self.mode)
+        return objs, M.get_best_ids_all_metrics(objs, opt_obj)
+
     def guided_sample(self, batch_idx, batch_size, noise, save_dir=None, opt_obj="rotate", ori_range=[-1.0, 1.0],
                       unguided_sample=None, top_k: int = 1, trace: Optional[list] = None):
         """Per-object guided sampling (diffusion.py:541-576): every object restarts from the same ``noise``.

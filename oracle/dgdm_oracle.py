@@ -575,6 +575,22 @@ class OracleSampler:
             sample, _ = self._step(sample, int(t), torch.zeros_like(sample), 0.0)
         return sample
 
+    def denoise_from_data(self, data: Tensor, seed: int = 0) -> Dict[str, float]:
+        """generator/diffusion.py:179-201, 230-244: noise the data at t = num_inference_steps, run the unguided
+        schedule, report the three validation metrics."""
+        B = data.shape[0]
+        noise = torch.from_numpy(np.random.RandomState(seed).randn(*data.shape)).float()
+        a = self.alphas_cumprod[self.n_inf]
+        sample = a ** 0.5 * data + (1 - a) ** 0.5 * noise               # DDIMScheduler.add_noise
+        npl = 0.0
+        with torch.no_grad():
+            for t in self.timesteps:
+                eps = unet1d_forward(self.unet_sd, sample, torch.full((B,), int(t), dtype=torch.int64))
+                npl += F.mse_loss(eps, noise).item()
+                sample = ddim_step(eps, int(t), sample, self.alphas_cumprod, self.T, self.n_inf)
+        return {"val/noise pred loss": npl / self.n_inf, "val/denoise loss": F.mse_loss(sample, data).item(),
+                "val/accuracy": torch.mean((torch.abs(sample - data) < 0.01).float()).item()}
+
     # -- predicted task score and best-of-N (SURVEY.md §8c last row) -----------------------
     def score(self, designs: Tensor, obj_idx: int, opt_obj: str, ori_range=(-1.0, 1.0)) -> Tensor:
         """score[cand] = mean over the ``grid_size`` profile orientations of the objective."""

@@ -355,6 +355,25 @@ def test_guided_loop_3d_golden(g3, precision):
         grad_close(rec["grad"][0], g3[f"loop_grad_s{i}"], tol_for(precision, 12), f"3d loop s{i}")
 
 
+# ---------------------------------------------------------------------------------------------- f-1 / f-3
+def test_denoise_from_data_and_predicted_tables(g2):
+    objs = torch.from_numpy(g2["objects"])
+    dm = make2d("fp32", objs, int(g2["grid_size"]), int(g2["num_pos"]))
+    samp = orc.OracleSampler("point", syn.unet1d_state_dict(0), syn.dynamics2d_state_dict(0), objs, 6, 2)
+    data = torch.clamp(0.5 * syn.initial_noise(8, 14, seed=4), -1, 1)
+    got, want = dm.denoise_from_data(data, seed=0), samp.denoise_from_data(data, seed=0)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-3 * max(1.0, abs(want[k])), (k, got[k], want[k])
+    # predicted objective tables: same classes / best ids as computed from the oracle's profile pass
+    from dgdm_b200 import metrics as M
+    final = torch.from_numpy(g2["loop_rotate_clockwise_sample_o0_s4"])
+    o_gpu, best_gpu = dm.predicted_objectives(final, dm.object_vertices[0], "rotate_clockwise")
+    lg = samp.profile_logits(final, 0).permute(1, 0, 2).numpy()
+    o_cpu = M.predicted_objectives(lg, "rotate_clockwise")
+    assert [o["num_clockwise_classes"] for o in o_gpu] == [o["num_clockwise_classes"] for o in o_cpu]
+    assert best_gpu == M.get_best_ids_all_metrics(o_cpu, "rotate_clockwise")
+
+
 # ---------------------------------------------------------------------------------------------- K6
 def test_best_of_n_ties_nan_and_topk():
     dm = make2d("fp32_simt", syn.objects_2d(1), 2, 1)
