@@ -7,10 +7,10 @@
 // CUDA-core GEMM (GemmArgs, common.cuh) -- no im2col.
 //
 // One persistent CTA per SM, 14 warps, 128 output rows per tile, all N (128 or 256) columns per tile:
-//   warps 4-11 A producers: each thread owns half a row of the tile; per 64-wide k-block it loads 128 contiguous
-//              bytes of fp32 (one tap, 32 channels), splits to bf16 hi/lo and writes its half of the 128-byte row into shared
-//              memory in the canonical K-major SWIZZLE_128B layout (16-byte chunk j of row r at chunk j^(r&7)),
-//              then fence.proxy.async + mbarrier arrive.
+//   warps 4-11 A producers: per 64-wide k-block the 256 threads read the [128 x 64] fp32 block with coalesced
+//              128-bit loads (lanes along K), split to bf16 hi/lo and write it into shared memory in the canonical
+//              K-major SWIZZLE_128B layout (16-byte chunk j of row r at chunk j^(r&7)), then fence.proxy.async +
+//              mbarrier arrive; loads run one k-block ahead of the conversion.
 //   warp 12    W producer: cp.async.bulk (TMA unit) of the pre-packed, pre-swizzled weight tiles (gemm_tc_pack).
 //   warp 13    MMA issuer: tcgen05.mma.cta_group::1.kind::f16, A and B from shared memory, M=128 x N x K=16,
 //              fp32 accumulators in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i overlaps
@@ -114,44 +114,61 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
 
   if (warp >= 4 && warp < 12) {
     // ------------------------------- A producers -------------------------------
-    // warp pair (p, p+4) shares 32 rows: each thread converts half a 64-wide k-block row (32 fp32 = 128 B)
-    const int pw = warp - 4;
-    const int r = (pw & 3) * 32 + lane;            // row of the tile owned by this thread
-    const int half = pw >> 2;                      // which 32-element half of the k-block row
+    // 256 producer threads tile a [128 rows x 64 fp32] k-block as 16 float4 columns x 16 row groups: lane -> float4
+    // column (+16 lanes -> next row), so a warp reads two contiguous 256-byte row segments per load instead of 32
+    // scattered lines with a thread-per-row mapping (the L1TEX pipe was the limiter: ncu "Mem Busy" 75%).
+    // Each thread owns column c4 of rows rg, rg+16, ..., rg+112; row offsets are computed once per tile.
+    const int pt = (warp - 4) * 32 + lane;         // 0..255
+    const int c4 = pt & 15, rg = pt >> 4;
     uint32_t stage = 0, phase = 0;
     for (int t = 0; t < my_tiles; ++t) {
-      const int64_t m = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TM + r;
-      const bool live = m < g.M;
-      const float* arow = g.A + (live ? (m / g.a_lr) * g.a_ss + (m % g.a_lr) * g.a_rs : 0);
-      for (int kb = 0; kb < P.n_kb; ++kb) {
-        const int k0 = kb * KB;
-        const float* src = arow + (int64_t)(k0 / g.a_ct) * g.a_ts + (k0 % g.a_ct) + half * 32;
-        float4 v[8];
+      const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TM;
+      int64_t roff[8];
+      uint32_t live = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = live ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + rg + 16 * i;
+        const bool ok = m < g.M;
+        live |= (ok ? 1u : 0u) << i;
+        roff[i] = ok ? (m / g.a_lr) * g.a_ss + (m % g.a_lr) * g.a_rs + c4 * 4 : 0;
+      }
+      auto load8 = [&](int kb, float4 (&v)[8]) {
+        const int k0 = kb * KB;
+        const float* base = g.A + (int64_t)(k0 / g.a_ct) * g.a_ts + (k0 % g.a_ct);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[i] = (live >> i) & 1u ? __ldg(reinterpret_cast<const float4*>(base + roff[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto convert_store = [&](const float4 (&v)[8]) {
         bar_wait(&S.empty[stage], phase ^ 1, P.err, 11);
         uint8_t* st = ring + (size_t)stage * P.stage_bytes;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {             // 16-byte chunk j = 8 bf16 = two float4
-          const int j = half * 4 + jj;
-          const float f[8] = {v[2 * jj].x, v[2 * jj].y, v[2 * jj].z, v[2 * jj].w, v[2 * jj + 1].x, v[2 * jj + 1].y, v[2 * jj + 1].z, v[2 * jj + 1].w};
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-            float2 hf = __bfloat1622float2(h);
-            __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
-            hi[e] = *reinterpret_cast<uint32_t*>(&h);
-            lo[e] = *reinterpret_cast<uint32_t*>(&l);
+        for (int i = 0; i < 8; ++i) {
+          const int r = rg + 16 * i;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i].x, v[i].y), h1 = __floats2bfloat162_rn(v[i].z, v[i].w);
+          const uint32_t o = (uint32_t)r * 128u + (uint32_t)((((c4 >> 1) ^ (r & 7)) * 16) + (c4 & 1) * 8);
+          *reinterpret_cast<uint2*>(st + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          if (P.x3) {
+            float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            __nv_bfloat162 l0 = __floats2bfloat162_rn(v[i].x - f0.x, v[i].y - f0.y), l1 = __floats2bfloat162_rn(v[i].z - f1.x, v[i].w - f1.y);
+            *reinterpret_cast<uint2*>(st + off_alo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
           }
-          const uint32_t o = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) * 16);
-          *reinterpret_cast<uint4*>(st + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (P.x3) *reinterpret_cast<uint4*>(st + off_alo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
         if (lane == 0) bar_arrive(&S.full_a[stage]);
         if (++stage == (uint32_t)P.n_stage) { stage = 0; phase ^= 1; }
+      };
+      // loads run one k-block ahead of the convert/store (register double buffer)
+      float4 va[8], vb[8];
+      load8(0, va);
+      for (int kb = 0; kb < P.n_kb; kb += 2) {
+        if (kb + 1 < P.n_kb) load8(kb + 1, vb);
+        convert_store(va);
+        if (kb + 1 < P.n_kb) {
+          if (kb + 2 < P.n_kb) load8(kb + 2, va);
+          convert_store(vb);
+        }
       }
     }
   } else if (warp == 12) {

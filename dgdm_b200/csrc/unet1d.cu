@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(256) film_kernel(FilmArgs a, float t) {
     cond[tid] = mish(s);      // every cond_encoder starts with Mish (diffusion_utils.py:89-91)
   }
   __syncthreads();
-  for (int b = 0; b < 8; ++b) {
+  {
+    const int b = blockIdx.x;                 // one CTA per residual block (cond is recomputed per CTA: ~5k MACs)
     for (int j = tid; j < 2 * a.cout[b]; j += blockDim.x) {
       float s = a.film_b[b][j];
       for (int k = 0; k < DSED; ++k) s = fmaf(a.film_w[b][j * DSED + k], cond[k], s);
@@ -341,7 +342,7 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
     fa.film_w[b] = w->blocks[b].film_w; fa.film_b[b] = w->blocks[b].film_b; fa.cout[b] = w->blocks[b].cout;
     fa.film[b] = B.film[b];
   }
-  film_kernel<<<1, 256, 0, s>>>(fa, (float)t);
+  film_kernel<<<8, 256, 0, s>>>(fa, (float)t);
   DGDM_LAUNCH_CHECK();
   // pads must be zero; interiors are always fully overwritten before they are read
   DGDM_CUDA(cudaMemsetAsync(big, 0, bufs_floats(nc, L) * sizeof(float), s));
