@@ -210,7 +210,7 @@ __global__ void scale_kernel(float* __restrict__ out, const float* __restrict__ 
 inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 struct Hoist {
-  float *h0, *e, *U, *Cst, *V, *pose, *temb, *th, *te, *tc, *oh, *oc, *dUp, *dU, *de, *dh0, *score_sum;
+  float *h0, *e, *U, *Cst, *V, *Vt, *pose, *temb, *th, *te, *tc, *oh, *oc, *dUp, *dU, *de, *dh0, *score_sum;
   int G;
   int64_t n_pairs;
 };
@@ -221,7 +221,7 @@ size_t hoist_bytes(int P, int H1, int obj_dim, int64_t nd, int n_obj, int64_t n_
   auto a = [](size_t n) { return align_up(n * sizeof(float), 256); };
   size_t b = 0;
   b += a(nd * 256) * 2 + a(nd * H1);                     // h0, e, U
-  b += a((size_t)n_obj * H1) + a((size_t)G * H1) + a((size_t)G * 27);
+  b += a((size_t)n_obj * H1) + 2 * a((size_t)G * H1) + a((size_t)G * 27);
   b += a(256) * 3 + a(H1);                               // temb, th, te, tc
   b += a((size_t)n_obj * 256) * 2;                       // oh, oc
   b += a(n_pairs * H1) + a(nd * H1) + a(nd * 256) * 2;   // dUp, dU, de, dh0
@@ -263,6 +263,8 @@ int run_hoists(const dgdm_dyn_weights* w, const float* x, int nd, const float* o
   pose_embed_kernel<<<blocks_for(h.G, 128), 128, 0, s>>>(h.pose, *grid, h.G);
   DGDM_LAUNCH_CHECK();
   DGDM_TRY(gemm_f32(gemm_plain(h.pose, 27, w->w1_pose, nullptr, h.V, H1, h.G, H1, 27, ACT_NONE), s));
+  // the same table transposed ([H1][G]) for the tensor-core trunk's coalesced per-row reads
+  DGDM_TRY(gemm_f32(gemm_plain(w->w1_pose, 27, h.pose, nullptr, h.Vt, h.G, H1, h.G, 27, ACT_NONE), s));
   // time: 2D = MLP(SiLU) of a 128-d embedding; 3D = raw 256-d embedding (profile_forward_3d.py:83)
   const float* te;
   if (w->is_3d) {
@@ -299,6 +301,7 @@ int carve(const dgdm_dyn_weights* w, int nd, int n_obj, int opd, const dgdm_pose
   h.U = ar.take<float>((size_t)nd * H1);
   h.Cst = ar.take<float>((size_t)n_obj * H1);
   h.V = ar.take<float>((size_t)h.G * H1);
+  h.Vt = ar.take<float>((size_t)h.G * H1);
   h.pose = ar.take<float>((size_t)h.G * 27);
   h.temb = ar.take<float>(256);
   h.th = ar.take<float>(256);
@@ -379,7 +382,7 @@ int trunk_dispatch(const dgdm_dyn_weights* w, const Hoist& h, int nd, int n_obj,
   size_t need = tc_trunk_workspace_bytes(w->H1, h.n_pairs, h.G);
   void* tws = ar.take<char>(need);
   if (!ar.ok) { set_error("dynamics: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
-  return tc_trunk(w, h.U, h.Cst, h.V, nd, n_obj, opd, pair_object, h.G, obj, backward, h.dUp, h.score_sum, logits, tws,
+  return tc_trunk(w, h.U, h.Cst, h.Vt, nd, n_obj, opd, pair_object, h.G, obj, backward, h.dUp, h.score_sum, logits, tws,
                   need, precision, s);
 }
 
@@ -433,7 +436,7 @@ extern "C" int dgdm_dyn_forward_rows(const dgdm_dyn_weights* w, const float* x, 
   float* zeros = ar.take<float>(2 * (size_t)H1);
   h.score_sum = ar.take<float>(n);
   if (!ar.ok) { set_error("dgdm_dyn_forward_rows: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
-  h.Cst = zeros; h.V = zeros + H1;
+  h.Cst = zeros; h.V = zeros + H1; h.Vt = zeros + H1;
   DGDM_CUDA(cudaMemsetAsync(zeros, 0, 2 * (size_t)H1 * sizeof(float), s));
   // every encoder at row scale -- this is the un-hoistable "paired" mode of the forward signature
   DGDM_TRY(gemm_f32(gemm_plain(x, P, w->ge_w0, w->ge_b0, h.h0, 256, n, 256, P, ACT_RELU), s));

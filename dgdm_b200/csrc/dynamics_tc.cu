@@ -53,7 +53,7 @@ struct Seg {
 
 struct TcParams {
   const uint8_t* img;
-  const float* U; const float* Cst; const float* V;
+  const float* U; const float* Cst; const float* Vt;   // Vt: pose table transposed, [H1][G]
   const float* bias[7]; const float* w_out; const float* b_out;
   const int32_t* pair_object;
   float* part;          // [n_slots][H1] per-(pair,tile) partial column sums  (backward)
@@ -327,11 +327,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
       const int64_t pr = live ? r_glob / P.G : -1;
       const int g = live ? (int)(r_glob % P.G) : 0;
       const float coef = (live && P.obj.row_coef) ? P.obj.row_coef[r_glob] : 1.f;
-      const float* u_row = nullptr; const float* c_row = nullptr; const float* v_row = nullptr;
+      const float* u_row = nullptr; const float* c_row = nullptr;
       if (live) {
         u_row = P.U + (pr / P.opd) * P.H1;
         c_row = P.Cst + (int64_t)pair_obj(pr, P.opd, P.n_designs, P.n_obj, P.pair_object) * P.H1;
-        v_row = P.V + (int64_t)g * P.H1;
       }
       const int64_t p_first = ((int64_t)tile * TILE_M) / P.G;
       int64_t last_row = (int64_t)tile * TILE_M + TILE_M - 1;
@@ -361,14 +360,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           const int col0 = kh * 256 + kb * 64 + h * 32;
           float v[32];
           uint32_t bits = 0;
+          // The pose table is read TRANSPOSED ([H1][G]): lanes are consecutive pose rows g, so each feature is one
+          // coalesced 128-byte request; all 32 loads are issued before use.  U/Cst rows are warp-broadcast loads.
+          float pv[32];
+          {
+            const float* vt = P.Vt + (int64_t)col0 * P.G + g;
+            const uint32_t G32 = (uint32_t)P.G;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pv[i] = live ? __ldg(vt + i * G32) : 0.f;
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live) {
               float4 k4 = *reinterpret_cast<const float4*>(c_row + col0 + i);
               float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + i);
-              float4 v4 = *reinterpret_cast<const float4*>(v_row + col0 + i);
-              a.x = (k4.x + u4.x) + v4.x; a.y = (k4.y + u4.y) + v4.y; a.z = (k4.z + u4.z) + v4.z; a.w = (k4.w + u4.w) + v4.w;
+              a.x = (k4.x + u4.x) + pv[i]; a.y = (k4.y + u4.y) + pv[i + 1]; a.z = (k4.z + u4.z) + pv[i + 2]; a.w = (k4.w + u4.w) + pv[i + 3];
             }
             v[i] = fmaxf(a.x, 0.f); v[i + 1] = fmaxf(a.y, 0.f); v[i + 2] = fmaxf(a.z, 0.f); v[i + 3] = fmaxf(a.w, 0.f);
             bits |= (a.x > 0.f ? 1u : 0u) << i | (a.y > 0.f ? 1u : 0u) << (i + 1) | (a.z > 0.f ? 1u : 0u) << (i + 2) |
@@ -652,7 +659,7 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   Plan pl = make_plan(w, H1);
   TcParams P{};
   P.img = (const uint8_t*)w->tc_image;
-  P.U = U; P.Cst = Cst; P.V = V;
+  P.U = U; P.Cst = Cst; P.Vt = V;
   for (int i = 0; i < 7; ++i) P.bias[i] = w->bl[i];
   P.w_out = w->w_out; P.b_out = w->b_out;
   P.pair_object = pair_object;
