@@ -150,10 +150,12 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = n_obj_s * b_s * args.steps / dt
     sample = f"{n_obj_s} object x {b_s} candidates x {GRID * NPOS * NPOS} pose rows x {T_INF} steps + scoring, per step"
-    line = {"impl": "reference", "metric": "guided designs/sec", "value": val, "unit": "designs/s", "n_gpus": 0,
+    line = {"impl": "reference", "metric": "guided designs/sec", "value": val, "unit": "designs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1, "cpu"),
+            "config": dict(workload_config(args.gpus, args.precision),
+                           reference_arm="CPU oracle port of the reference sampler, host cores only; each step is the "
+                                         "bounded sample in cpu_baseline.sample"),
             "cpu_baseline": {"value": val, "unit": "designs/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": "designs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

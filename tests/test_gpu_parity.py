@@ -428,3 +428,56 @@ def test_full_size_properties_2d(precision):
     assert rel(g_cu, exact) < TOL[precision]
     per = (g_cu - exact).norm(dim=1) / exact.norm(dim=1)
     print(f"[{precision}] aggregate rel-err {rel(g_cu, exact):.3e}, worst candidate {float(per.max()):.3e}")
+
+
+@pytest.mark.parametrize("precision", TC_MODES)
+def test_full_size_properties_3d(precision):
+    """C3-shaped slice (128 candidates x 1125 pose rows per object, 512-wide layer 1 => split-K / split-N segments):
+    tensor-core modes against the exact-fp32 CUDA-core path at the north-star bounds, no scaling."""
+    n_obj, B, grid, npos = 2, 128, 45, 5
+    objs, st = syn.objects_3d(n_obj), syn.fps_starts(n_obj)
+    dm = make3d(precision, objs, st, grid, npos)
+    ref = make3d("fp32_simt", objs, st, grid, npos)
+    x = syn.initial_noise(B, 42)[..., 0].cuda().repeat(n_obj, 1).contiguous()
+    for name in ("rotate_clockwise", "rotate"):
+        g = dm.guidance(x, 6, dm._obj_dev, 1, name)
+        exact = ref.guidance(x, 6, ref._obj_dev, 1, name)
+        r = rel(g, exact)
+        per = (g - exact).norm(dim=1) / exact.norm(dim=1)
+        print(f"[3d {precision} {name}] aggregate rel-err {r:.3e}, worst candidate {float(per.max()):.3e}")
+        assert r < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", TC_MODES)
+def test_full_run_scores_and_selection_2d(precision):
+    """A complete guided-sampling run on a C2-shaped slice (4 objects x 256 candidates x 900 pose rows x 5 steps):
+    final designs, predicted scores and best-of-N of the tensor-core modes against the exact-fp32 GPU path.
+    Scores must agree to 1e-3; the selected design must be identical whenever the exact run's margin between its
+    best and second-best score exceeds twice the score tolerance (otherwise the two are a tie at this precision)."""
+    n_obj, B, grid, npos = 4, 256, 36, 5
+    objs = syn.objects_2d(n_obj)
+    noise = syn.initial_noise(B, 14)
+    out = make2d(precision, objs, grid, npos).guided_sample(0, B, noise, opt_obj="rotate_clockwise", top_k=2)
+    ref = make2d("fp32_simt", objs, grid, npos).guided_sample(0, B, noise, opt_obj="rotate_clockwise", top_k=2)
+    d_err = rel(out["designs"], ref["designs"])
+    s_err = float((out["scores"] - ref["scores"]).abs().max())
+    stol = 1e-3 if precision == "fp32" else 2e-2
+    print(f"[{precision}] designs rel-err {d_err:.3e}, scores max abs-err {s_err:.3e}")
+    assert d_err < (1e-3 if precision == "fp32" else 2e-2) and s_err < stol
+    margin = (ref["best_scores"][:, 0] - ref["best_scores"][:, 1]).cpu().numpy()
+    same = (out["best_ids"][:, 0] == ref["best_ids"][:, 0]).cpu().numpy()
+    for o in range(n_obj):
+        assert same[o] or margin[o] <= 2 * stol, (o, margin[o])
+    if precision == "fp32":
+        assert same.all(), margin
+
+
+def test_guided_sampling_is_deterministic():
+    """Bit-identical results run to run (fixed-order slot reduction, no atomics)."""
+    objs = syn.objects_2d(3)
+    dm = make2d("fp32", objs, 36, 5)
+    noise = syn.initial_noise(64, 14)
+    a = dm.guided_sample(0, 64, noise, opt_obj="clockwise_up")
+    b = dm.guided_sample(0, 64, noise, opt_obj="clockwise_up")
+    assert torch.equal(a["designs"], b["designs"]) and torch.equal(a["scores"], b["scores"])
+    assert torch.equal(a["best_ids"], b["best_ids"])
