@@ -54,7 +54,11 @@ struct Arena {
   char* base;
   size_t cap, off;
   bool ok;
-  Arena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0), ok(true) {}
+  // the caller's pointer is rounded up to 256 bytes; the *_workspace_bytes() queries include that slack
+  Arena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0), ok(p != nullptr) {
+    size_t mis = (size_t)((uintptr_t)p & 255);
+    if (mis) { size_t adj = 256 - mis; if (adj > cap) { ok = false; } else { base += adj; cap -= adj; } }
+  }
   template <typename T>
   T* take(size_t count) {
     size_t bytes = align_up(count * sizeof(T), 256);

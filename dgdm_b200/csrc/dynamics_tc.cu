@@ -648,14 +648,19 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   int* err = ar.take<int>(1);
   if (!ar.ok) { set_error("tc_trunk: workspace too small"); return DGDM_EWORKSPACE; }
 
-  static thread_local int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    DGDM_CUDA(cudaGetDevice(&dev));
-    DGDM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  // per-device one-time setup (one process normally drives one GPU, but do not assume it)
+  static int sm_counts[64] = {0};
+  int dev = 0;
+  DGDM_CUDA(cudaGetDevice(&dev));
+  DGDM_CHECK_ARG(dev >= 0 && dev < 64, "tc_trunk: device ordinal %d out of range", dev);
+  if (sm_counts[dev] == 0) {
+    int n = 0;
+    DGDM_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    sm_counts[dev] = n;
   }
+  const int sm_count = sm_counts[dev];
   Plan pl = make_plan(w, H1);
   TcParams P{};
   P.img = (const uint8_t*)w->tc_image;

@@ -305,13 +305,17 @@ int gemm_tc_pack(const float* W, int N, int K, void* image, cudaStream_t s) {
 // err: device int for the bounded-wait error code (may be nullptr)
 int gemm_tc(const GemmArgs& g, const void* wimg, int x3, int* err, cudaStream_t s) {
   DGDM_CHECK_ARG(gemm_tc_eligible(g), "gemm_tc: shape not eligible (N=%d K=%d a_ct=%d)", g.N, g.K, g.a_ct);
-  static thread_local int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    DGDM_CUDA(cudaGetDevice(&dev));
-    DGDM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  static int sm_counts[64] = {0};
+  int dev = 0;
+  DGDM_CUDA(cudaGetDevice(&dev));
+  DGDM_CHECK_ARG(dev >= 0 && dev < 64, "gemm_tc: device ordinal %d out of range", dev);
+  if (sm_counts[dev] == 0) {
+    int n = 0;
+    DGDM_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     DGDM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048 + (int)sizeof(Bars)));
+    sm_counts[dev] = n;
   }
+  const int sm_count = sm_counts[dev];
   TcGemmParams P{};
   P.g = g; P.wimg = (const uint8_t*)wimg; P.err = err; P.x3 = x3;
   P.n_tiles = (int)((g.M + TM - 1) / TM);
