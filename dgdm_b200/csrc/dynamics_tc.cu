@@ -10,14 +10,14 @@
 // = 2*2*(7*256^2 + 256*3) = 1 838 080 FLOP per row (2D), none of it ever touching HBM: the row's activations
 // live in TMEM, only ReLU sign bits (32 B per layer per row) are kept, in shared memory.
 //
-// Mapping to the SM (one persistent CTA per SM, 10 warps):
-//   warp 8   producer: streams weight tiles global(L2) -> smem ring with cp.async.bulk (TMA unit, UBLKCP),
+// Mapping to the SM (one persistent CTA per SM, 18 warps):
+//   warp 16  producer: streams weight tiles global(L2) -> smem ring with cp.async.bulk (TMA unit, UBLKCP),
 //            completion on mbarriers.  Tiles are pre-swizzled (128B swizzle, K-major) by dgdm_dyn_pack_tc so
 //            the bytes land exactly in the canonical UMMA layout.
-//   warp 9   MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16, M=128 (tile rows) x N=256 x K=16,
+//   warp 17  MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16, M=128 (tile rows) x N=256 x K=16,
 //            A operand from TMEM (the activations), B from smem (the weight tile), D (fp32) in TMEM;
 //            tcgen05.commit releases smem stages and signals the epilogue.
-//   warps 0-7 epilogue: tcgen05.ld the accumulator, bias + ReLU (or ReLU-mask in the backward), collect
+//   warps 0-15 epilogue: tcgen05.ld the accumulator, bias + ReLU (or ReLU-mask in the backward), collect
 //            sign bits, convert to bf16 (hi [+ lo]) and tcgen05.st it back as the next layer's A operand.
 //            The last backward layer is reduced over the tile's rows per pair with warp shuffles and written
 //            to a per-(pair,tile) slot; a small second kernel adds the slots in fixed order (deterministic).
@@ -39,7 +39,8 @@ constexpr int TILE_M = 128;
 constexpr int KBLK = 64;                       // bf16 elements per k-block row = 128 bytes = one swizzle span
 constexpr int WTILE_BYTES = 256 * KBLK * 2;    // 32 KB: 256 rows x 128 B
 constexpr int NSTAGE = 5;
-constexpr int NTHREADS = 320;
+constexpr int NEPI = 16;                       // epilogue warps: 4 per TMEM lane quadrant, 16 features of every k-block each
+constexpr int NTHREADS = (NEPI + 2) * 32;      // + producer warp + MMA warp
 constexpr int MAX_SEG = 20;
 constexpr int MASK_WORDS = 16 + 7 * 8;         // layer 1 up to 512 wide + 7 layers of 256
 
@@ -144,6 +145,22 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
                  "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                :: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -176,17 +193,61 @@ __device__ __forceinline__ int pair_obj(int64_t p, int opd, int n_designs, int n
 
 // Split 32 fp32 values into packed bf16 hi (and lo = rn(v - hi)) pairs; element 2i in the low half.
 template <bool X3>
-__device__ __forceinline__ void split_pack(const float (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+__device__ __forceinline__ void split_pack(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < 8; ++i) {
     __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     hi[i] = *reinterpret_cast<uint32_t*>(&h);
     if (X3) {
-      float2 hf = __bfloat1622float2(h);
-      __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+      // unpack with a shift and a mask (no PRMT pair): fewer ops on the half-rate ALU pipe
+      const float h0 = __uint_as_float(hi[i] << 16), h1 = __uint_as_float(hi[i] & 0xFFFF0000u);
+      __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
       lo[i] = *reinterpret_cast<uint32_t*>(&l);
     }
   }
+}
+
+// ---- ReLU + split + sign bits with the conversion unit doing the ReLU ------------------------------------------
+// The epilogue is bound by the half-rate ALU pipe (FSETP/SEL/FMNMX/PRMT...), not by TMEM or latency, so the
+// forward path avoids it: cvt.{rz|rn}.relu.bf16x2 clamps negatives while converting, the lo residual
+// (z - float(hi), >= 0 for z >= 0 because hi is truncated, negative for z < 0) goes through the same .relu
+// conversion, and the 16 sign bits are read off the exponent bytes of the packed hi words, four elements at a time.
+__device__ __forceinline__ uint32_t cvt_rz_relu_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_rn_relu_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+// bit position of element e (0..15) inside the 16-bit sign word produced by relu_split16
+__host__ __device__ constexpr int mask_pos(int e) { return ((e & 1) * 8) + (((e >> 1) & 1) * 4) + 3 - (e >> 2); }
+
+// z[16] (pre-activation) -> packed bf16 hi[8] (+ lo[8]) of relu(z), returns the 16 sign bits (mask_pos layout).
+// A value whose bf16 exponent field is < 2 (|z| < 2^-125) counts as zero.
+template <bool X3>
+__device__ __forceinline__ uint32_t relu_split16(const float (&z)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (X3) {
+      hi[i] = cvt_rz_relu_bf16x2(z[2 * i], z[2 * i + 1]);
+      const float h0 = __uint_as_float(hi[i] << 16), h1 = __uint_as_float(hi[i] & 0xFFFF0000u);
+      lo[i] = cvt_rn_relu_bf16x2(z[2 * i] - h0, z[2 * i + 1] - h1);
+    } else {
+      hi[i] = cvt_rn_relu_bf16x2(z[2 * i], z[2 * i + 1]);
+    }
+  }
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // exponent bytes of elements 4k..4k+3 -> one word; byte != 0  <=>  (byte + 0x7F) has its MSB set
+    const uint32_t t = __byte_perm(hi[2 * k], hi[2 * k + 1], 0x7531) + 0x7F7F7F7Fu;
+    m |= (t & 0x80808080u) >> k;
+  }
+  m >>= 4;                                         // flags now at bits {0..3, 8..11, 16..19, 24..27}
+  return (m | (m >> 12)) & 0xFFFFu;
 }
 
 // Column sums over the 32 lanes of a warp for 32 per-lane values: after the butterfly lane i holds
@@ -213,7 +274,7 @@ struct Smem {
   float b_out[4];
   float red[4][256];            // per lane-quadrant partial column sums
   float red_s[4];
-  uint32_t mask[MASK_WORDS][TILE_M];
+  uint16_t mask[2 * MASK_WORDS][TILE_M];      // ReLU sign bits, one halfword per (16-feature group, row)
 };
 
 template <bool X3>
@@ -227,14 +288,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    for (int k = 0; k < 4; ++k) mbar_init(&S.a_ready[k], 8);
+    for (int k = 0; k < 4; ++k) mbar_init(&S.a_ready[k], NEPI);
     mbar_init(&S.d_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 7 * 256; i += NTHREADS) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256];
   for (int i = tid; i < 3 * 256; i += NTHREADS) S.w_out[i / 256][i % 256] = P.w_out[i];
   if (tid < 3) S.b_out[tid] = P.b_out[tid];
-  if (warp == 9) {
+  if (warp == NEPI + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -246,7 +307,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
   const int tiles_mine = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tiles_per_seg = X3 ? 8 : 4;       // weight tiles per segment: 4 k-blocks x (hi [, lo])
 
-  if (warp == 8) {
+  if (warp == NEPI) {
     // =============================== producer ===============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -266,7 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == NEPI + 1) {
     // =============================== MMA issuer ===============================
     // TMEM is two 256-column regions.  During a segment the A operand lives in region `cur` (per 64-wide
     // k-block kb: hi at [64kb, 64kb+32), lo at [64kb+32, 64kb+64)) and the accumulator in the other one.
@@ -309,16 +370,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
       }
     }
   } else {
-    // =============================== epilogue warps 0..7 ===============================
-    // warp (q, h): TMEM lane quadrant q (rows 32q..32q+31); of every 64-feature k-block it owns the 32-feature
-    // half h.  The two warps of a quadrant share lanes, so they meet on a named barrier before overwriting
-    // accumulator columns the other one still has to read.
-    const int q = warp & 3, h = warp >> 2;
+    // =============================== epilogue warps 0..15 ===============================
+    // warp (q, hq): TMEM lane quadrant q (rows 32q..32q+31); of every 64-feature k-block it owns the 16 features
+    // [16hq, 16hq+16).  Four warps per scheduler keep the issue slots busy while a sibling waits on a TMEM load, a
+    // named barrier or tcgen05.wait::st (with two lock-stepped warps per scheduler the epilogue was latency-bound
+    // at ~1100 cycles per k-block).  The four warps of a quadrant share lanes, so they meet on a 128-thread named
+    // barrier before overwriting accumulator columns a sibling still has to read.
+    const int q = warp & 3, hq = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-    const int l1_words = P.H1 / 32;
+    const int l1_hw = P.H1 / 16;                  // halfwords of layer-1 sign bits per row
     uint32_t d_phase = 0;
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); };
+    auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); };
 
     for (int t = 0; t < tiles_mine; ++t) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
@@ -345,44 +408,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.a_ready[kb]);
       };
-      // store 32 features (k-block kb, half h) of this row as bf16 hi [+ lo] into region `reg`
-      auto store_a = [&](uint32_t reg, int kb, const float (&v)[32]) {
-        uint32_t hi[16], lo[16];
+      // store 16 features (k-block kb, group hq) of this row as bf16 hi [+ lo] into region `reg`
+      auto store_packed = [&](uint32_t reg, int kb, const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
+        const uint32_t col = reg * 256u + (uint32_t)(kb * 64 + hq * 8);
+        tmem_st8(lane_addr + col, hi);
+        if (X3) tmem_st8(lane_addr + col + 32, lo);
+      };
+      auto store_a = [&](uint32_t reg, int kb, const float (&v)[16]) {
+        uint32_t hi[8], lo[8];
         split_pack<X3>(v, hi, lo);
-        const uint32_t col = reg * 256u + (uint32_t)(kb * 64 + h * 16);
-        tmem_st16(lane_addr + col, hi);
-        if (X3) tmem_st16(lane_addr + col + 32, lo);
+        store_packed(reg, kb, hi, lo);
       };
       // layer-1 activations for K-half `kh` -> A operand in region `reg` + layer-1 sign bits
       auto build_a1 = [&](int kh, uint32_t reg) {
 #pragma unroll 1
         for (int kb = 0; kb < 4; ++kb) {
-          const int col0 = kh * 256 + kb * 64 + h * 32;
-          float v[32];
-          uint32_t bits = 0;
+          const int col0 = kh * 256 + kb * 64 + hq * 16;
+          float z[16];
           // The pose table is read TRANSPOSED ([H1][G]): lanes are consecutive pose rows g, so each feature is one
-          // coalesced 128-byte request; all 32 loads are issued before use.  U/Cst rows are warp-broadcast loads.
-          float pv[32];
+          // coalesced 128-byte request; all loads are issued before use.  U/Cst rows are warp-broadcast loads.
+          float pv[16];
           {
             const float* vt = P.Vt + (int64_t)col0 * P.G + g;
             const uint32_t G32 = (uint32_t)P.G;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pv[i] = live ? __ldg(vt + i * G32) : 0.f;
+            for (int i = 0; i < 16; ++i) pv[i] = live ? __ldg(vt + i * G32) : 0.f;
           }
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < 16; i += 4) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live) {
               float4 k4 = *reinterpret_cast<const float4*>(c_row + col0 + i);
               float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + i);
               a.x = (k4.x + u4.x) + pv[i]; a.y = (k4.y + u4.y) + pv[i + 1]; a.z = (k4.z + u4.z) + pv[i + 2]; a.w = (k4.w + u4.w) + pv[i + 3];
             }
-            v[i] = fmaxf(a.x, 0.f); v[i + 1] = fmaxf(a.y, 0.f); v[i + 2] = fmaxf(a.z, 0.f); v[i + 3] = fmaxf(a.w, 0.f);
-            bits |= (a.x > 0.f ? 1u : 0u) << i | (a.y > 0.f ? 1u : 0u) << (i + 1) | (a.z > 0.f ? 1u : 0u) << (i + 2) |
-                    (a.w > 0.f ? 1u : 0u) << (i + 3);
+            z[i] = a.x; z[i + 1] = a.y; z[i + 2] = a.z; z[i + 3] = a.w;
           }
-          S.mask[kh * 8 + kb * 2 + h][row] = bits;
-          store_a(reg, kb, v);
+          uint32_t hi[8], lo[8];
+          S.mask[kh * 16 + kb * 4 + hq][row] = (uint16_t)relu_split16<X3>(z, hi, lo);
+          store_packed(reg, kb, hi, lo);
           signal_kb(kb);
         }
       };
@@ -402,37 +466,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           build_a1(1, cur);                         // second K-half of a1 replaces the first; accumulator stays
         } else if (sgm.kind == K_FWD || sgm.kind == K_BWD) {
           // FWD: a = relu(D + b), record sign bits of this layer.   BWD: d = D * 1[a_{layer} > 0].
-          const int mbase = sgm.layer == 0 ? 0 : l1_words + (sgm.layer - 1) * 8;
-          uint32_t rr[2][32];
-          tmem_ld32_async(d_addr + (uint32_t)(h * 32), rr[0]);
+          const int mbase = sgm.layer == 0 ? 0 : l1_hw + (sgm.layer - 1) * 16;
+          uint32_t rr[2][16];
+          tmem_ld16_async(d_addr + (uint32_t)(hq * 16), rr[0]);
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
-            tmem_ld_wait32(rr[kb & 1]);
-            if (kb + 1 < 4) tmem_ld32_async(d_addr + (uint32_t)((kb + 1) * 64 + h * 32), rr[(kb + 1) & 1]);
-            pair_sync();                            // both halves of k-block kb are now in registers
-            float v[32];
+            tmem_ld_wait16(rr[kb & 1]);
+            if (kb + 1 < 4) tmem_ld16_async(d_addr + (uint32_t)((kb + 1) * 64 + hq * 16), rr[(kb + 1) & 1]);
+            quad_sync();                            // all four 16-feature groups of k-block kb are now in registers
             if (sgm.kind == K_FWD) {
-              const float4* b4 = reinterpret_cast<const float4*>(&S.bias[sgm.layer - 1][kb * 64 + h * 32]);
-              uint32_t bits = 0;
+              const float4* b4 = reinterpret_cast<const float4*>(&S.bias[sgm.layer - 1][kb * 64 + hq * 16]);
+              float z[16];
 #pragma unroll
-              for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 bb = b4[i4];               // 128-bit broadcast load: 8 instead of 32 LSU ops
-                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int i = i4 * 4 + e;
-                  float z = __uint_as_float(rr[kb & 1][i]) + bv[e];
-                  bits |= (z > 0.f ? 1u : 0u) << i;
-                  v[i] = fmaxf(z, 0.f);
-                }
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 bb = b4[i4];
+                z[i4 * 4 + 0] = __uint_as_float(rr[kb & 1][i4 * 4 + 0]) + bb.x;
+                z[i4 * 4 + 1] = __uint_as_float(rr[kb & 1][i4 * 4 + 1]) + bb.y;
+                z[i4 * 4 + 2] = __uint_as_float(rr[kb & 1][i4 * 4 + 2]) + bb.z;
+                z[i4 * 4 + 3] = __uint_as_float(rr[kb & 1][i4 * 4 + 3]) + bb.w;
               }
-              S.mask[mbase + kb * 2 + h][row] = bits;
+              uint32_t hi[8], lo[8];
+              S.mask[mbase + kb * 4 + hq][row] = (uint16_t)relu_split16<X3>(z, hi, lo);
+              store_packed(dreg, kb, hi, lo);       // in place: the accumulator region becomes the next A operand
             } else {
-              const uint32_t bits = S.mask[mbase + kb * 2 + h][row];
+              const uint32_t bits = S.mask[mbase + kb * 4 + hq][row];
+              float v[16];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? __uint_as_float(rr[kb & 1][i]) : 0.f;
+              for (int i = 0; i < 16; ++i) v[i] = (bits >> mask_pos(i)) & 1u ? __uint_as_float(rr[kb & 1][i]) : 0.f;
+              store_a(dreg, kb, v);
             }
-            store_a(dreg, kb, v);                   // in place: the accumulator region becomes the next A operand
             signal_kb(kb);
           }
           cur ^= 1;
@@ -441,7 +503,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           tmem_ld8(d_addr, rr);
           const float l0 = __uint_as_float(rr[0]) + S.b_out[0], l1 = __uint_as_float(rr[1]) + S.b_out[1],
                       l2 = __uint_as_float(rr[2]) + S.b_out[2];
-          if (h == 0 && live && P.logits) {
+          if (hq == 0 && live && P.logits) {
             float* o = P.logits + r_glob * 3;
             o[0] = l0; o[1] = l1; o[2] = l2;
           }
@@ -449,37 +511,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             // forward only: per-pair sums of the objective over this tile's rows -> score_part[p + tile]
             const float val = live ? coef * (P.obj.c[0] * l0 + P.obj.c[1] * l1 + P.obj.c[2] * l2 + P.obj.sq0 * l0 * l0) : 0.f;
             if (P.G == 1) {                         // explicit-row mode: one row per pair, nothing to reduce
-              if (h == 0 && live) P.score_part[pr + tile] = val;
+              if (hq == 0 && live) P.score_part[pr + tile] = val;
             } else
             for (int64_t ps = p_first; ps <= p_last; ++ps) {
               float s = (pr == ps) ? val : 0.f;
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-              if (h == 0 && lane == 0) S.red_s[q] = s;
-              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (hq == 0 && lane == 0) S.red_s[q] = s;
+              asm volatile("bar.sync 1, 512;" ::: "memory");
               if (tid == 0) P.score_part[ps + tile] = (S.red_s[0] + S.red_s[1]) + (S.red_s[2] + S.red_s[3]);
-              asm volatile("bar.sync 1, 256;" ::: "memory");
+              asm volatile("bar.sync 1, 512;" ::: "memory");
             }
           } else {
             // seed of the backward pass: d8 = (dObj/dlogits . W_out) * 1[a_8 > 0], written over the logits' region
             const float dl0 = coef * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = coef * P.obj.c[1], dl2 = coef * P.obj.c[2];
-            const int mbase = l1_words + 6 * 8;
-            pair_sync();                            // the other half has read the logits too
+            const int mbase = l1_hw + 6 * 16;
+            quad_sync();                            // the sibling warps have read the logits too
 #pragma unroll 1
             for (int kb = 0; kb < 4; ++kb) {
-              const int col0 = kb * 64 + h * 32;
-              const uint32_t bits = S.mask[mbase + kb * 2 + h][row];
-              float v[32];
+              const int col0 = kb * 64 + hq * 16;
+              const uint32_t bits = S.mask[mbase + kb * 4 + hq][row];
+              float v[16];
               const float4* w0 = reinterpret_cast<const float4*>(&S.w_out[0][col0]);
               const float4* w1 = reinterpret_cast<const float4*>(&S.w_out[1][col0]);
               const float4* w2 = reinterpret_cast<const float4*>(&S.w_out[2][col0]);
 #pragma unroll
-              for (int i4 = 0; i4 < 8; ++i4) {
+              for (int i4 = 0; i4 < 4; ++i4) {
                 const float4 a0 = w0[i4], a1 = w1[i4], a2 = w2[i4];
                 const float d[4] = {dl0 * a0.x + dl1 * a1.x + dl2 * a2.x, dl0 * a0.y + dl1 * a1.y + dl2 * a2.y,
                                     dl0 * a0.z + dl1 * a1.z + dl2 * a2.z, dl0 * a0.w + dl1 * a1.w + dl2 * a2.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[i4 * 4 + e] = (bits >> (i4 * 4 + e)) & 1u ? d[e] : 0.f;
+                for (int e = 0; e < 4; ++e) v[i4 * 4 + e] = (bits >> mask_pos(i4 * 4 + e)) & 1u ? d[e] : 0.f;
               }
               store_a(dreg, kb, v);
               signal_kb(kb);
@@ -487,39 +549,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             cur ^= 1;
           }
         } else {   // K_LAST: d1 = D * 1[a_1 > 0], summed over the rows of each pair present in the tile (K2)
+          // warp (q, hq) reduces accumulator columns [64hq, 64hq+64) as two 32-column chunks
           if (P.G == 1) {                           // explicit-row mode: the row IS the pair; store it directly
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
+              const int cc = hq * 2 + c;              // 32-feature chunk index 0..7
               uint32_t rr[32];
-              tmem_ld32(d_addr + (uint32_t)(h * 128 + c * 32), rr);
+              tmem_ld32(d_addr + (uint32_t)(cc * 32), rr);
               if (live) {
-                const uint32_t bits = S.mask[sgm.half * 8 + h * 4 + c][row];
-                float4* o = reinterpret_cast<float4*>(P.part + (pr + tile) * P.H1 + sgm.half * 256 + h * 128 + c * 32);
+                const uint32_t b0 = S.mask[(sgm.half * 8 + cc) * 2][row], b1 = S.mask[(sgm.half * 8 + cc) * 2 + 1][row];
+                float4* o = reinterpret_cast<float4*>(P.part + (pr + tile) * P.H1 + sgm.half * 256 + cc * 32);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  o[i / 4] = make_float4((bits >> i) & 1u ? __uint_as_float(rr[i]) : 0.f, (bits >> (i + 1)) & 1u ? __uint_as_float(rr[i + 1]) : 0.f,
-                                         (bits >> (i + 2)) & 1u ? __uint_as_float(rr[i + 2]) : 0.f, (bits >> (i + 3)) & 1u ? __uint_as_float(rr[i + 3]) : 0.f);
+                for (int i = 0; i < 32; i += 4) {
+                  float e[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int ii = i + j;
+                    const uint32_t bit = ii < 16 ? (b0 >> mask_pos(ii)) & 1u : (b1 >> mask_pos(ii - 16)) & 1u;
+                    e[j] = bit ? __uint_as_float(rr[ii]) : 0.f;
+                  }
+                  o[i / 4] = make_float4(e[0], e[1], e[2], e[3]);
+                }
               }
             }
           } else
           for (int64_t ps = p_first; ps <= p_last; ++ps) {
             const bool mine = pr == ps;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
+              const int cc = hq * 2 + c;
               uint32_t rr[32];
-              tmem_ld32(d_addr + (uint32_t)(h * 128 + c * 32), rr);
-              const uint32_t bits = mine ? S.mask[sgm.half * 8 + h * 4 + c][row] : 0u;
+              tmem_ld32(d_addr + (uint32_t)(cc * 32), rr);
+              const uint32_t b0 = mine ? S.mask[(sgm.half * 8 + cc) * 2][row] : 0u, b1 = mine ? S.mask[(sgm.half * 8 + cc) * 2 + 1][row] : 0u;
               float v[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = (bits >> i) & 1u ? __uint_as_float(rr[i]) : 0.f;
-              S.red[q][h * 128 + c * 32 + lane] = warp_transpose_sum(v, lane);
+              for (int i = 0; i < 32; ++i)
+                v[i] = (i < 16 ? (b0 >> mask_pos(i)) & 1u : (b1 >> mask_pos(i - 16)) & 1u) ? __uint_as_float(rr[i]) : 0.f;
+              S.red[q][cc * 32 + lane] = warp_transpose_sum(v, lane);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            {
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (tid < 256) {
               const float s = (S.red[0][tid] + S.red[1][tid]) + (S.red[2][tid] + S.red[3][tid]);
               P.part[(ps + tile) * P.H1 + sgm.half * 256 + tid] = s;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
           }
           if (!last_seg) {                          // 3D: second N-half reuses the same A operand
 #pragma unroll 1
@@ -532,7 +605,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == NEPI + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
