@@ -51,6 +51,9 @@ def select_workload(name):
     if name == "c3":
         N_OBJ, N_CAND, GRID, NPOS, P, MODE = 64, 128, 45, 5, 42, "point_3d"
         WORKLOAD = "C3 (BASELINE.json configs[2])"
+    if name == "c2g36":   # the literal "x36 orientations" reading of configs[1]: num_pos = 1 => G = 36 (second point)
+        N_OBJ, N_CAND, GRID, NPOS, P, MODE = 64, 256, 36, 1, 14, "point"
+        WORKLOAD = "C2 literal reading (num_pos=1, 36 pose rows/candidate; denoiser ~45 % of FLOPs)"
     if name == "c5":   # 8 x B200 sweep: 1024 objects x 512 candidates => 128 objects per GPU (weak scaling below 8 GPUs)
         N_OBJ, N_CAND, GRID, NPOS, P, MODE = 128, 512, 45, 5, 42, "point_3d"
         WORKLOAD = "C5 (BASELINE.json configs[4], per-GPU shard of 1024 objects x 512 candidates)"
@@ -180,7 +183,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2g36", "c3", "c5"])
     args = ap.parse_args()
     select_workload(args.workload)
     if args.impl == "reference":
@@ -291,7 +294,7 @@ def main():
         peak = pk["bf16_sustained"] / (3.0 if x3 else 1.0)
         traffic = None                       # DRAM bytes per launch of this kernel from the committed ncu --set full capture
         tpath = os.path.join(REPO, "profiles", "tc_trunk_traffic.json")
-        if os.path.exists(tpath) and args.workload == "c2":
+        if os.path.exists(tpath) and args.workload == "c2":   # captured on C2 only
             traffic = json.load(open(tpath)).get("fp32" if x3 else "bf16", {}).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak if peak else None, "traffic": traffic,
