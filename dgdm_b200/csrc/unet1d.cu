@@ -9,7 +9,10 @@
 // sample of a step (generator/diffusion.py:572), so they are computed once per call by one small CTA.
 // The skip of down level 0 is pushed but never popped in the reference (diffusion_utils.py:264-275):
 // it is simply not kept.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace dgdm {
 // gemm_tc.cu
@@ -263,6 +266,322 @@ int res_block(const dgdm_unet_resblock& w, const float* film, const float* in, i
   return DGDM_OK;
 }
 
+
+// =================================================================================================
+// Tensor-core path (DGDM_PREC_BF16X3 / DGDM_PREC_BF16): activations live in HBM as bf16 hi/lo "chunk-major"
+// buffers (conv_tc.cuh) so every conv operand is moved by the TMA unit; GroupNorm reads the conv's fp32
+// "quad-major" output [C/4][n*L][4] and writes the next conv's operand directly.
+// =================================================================================================
+
+// First conv of the network (Cin = 1, k = 5): 5 MACs per output, CUDA cores.  out: fp32 quad-major.
+__global__ void __launch_bounds__(256) conv_in_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      int64_t n, int L, int C) {
+  const int64_t rows = n * L;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * (C / 4)) return;
+  const int quad = (int)(idx / rows);
+  const int64_t row = idx - (int64_t)quad * rows;
+  const int l = (int)(row % L);
+  float xv[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) { const int ll = l + t - 2; xv[t] = (ll >= 0 && ll < L) ? x[row + t - 2] : 0.f; }
+  float o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int co = quad * 4 + e;
+    float sacc = bias[co];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) sacc = fmaf(w[co * 5 + t], xv[t], sacc);
+    o[e] = sacc;
+  }
+  *reinterpret_cast<float4*>(out + idx * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+struct Gn2Args {
+  const float* in; int64_t in_rows;                          // fp32 quad-major [C/4][in_rows][4], row = b*L + l
+  const float* gamma; const float* beta; const float* film;  // film: [2C] (scale | shift) or null
+  int64_t n; int L, C;
+  int res_mode;                                              // 0 none, 1 chunk-major bf16, 2 fp32 quad-major, 3 Cin=1 1x1 conv of x
+  const uint8_t* r_hi; const uint8_t* r_lo; int64_t r_plane; int r_chunk0;
+  const float* r_f32;
+  const float* r_x; const float* r_w; const float* r_b;
+  int out_mode;                                              // 0 chunk-major, 1 even/odd positions split into two channel halves, 2 fused 1x1 output conv
+  uint8_t* o_hi; uint8_t* o_lo; int64_t o_plane; int o_chunk0;
+  const float* p_w; const float* p_b; float* eps;
+};
+
+// GroupNorm(8) + Mish (+ FiLM) (+ residual) for one sample per CTA, one warp per group.  A lane item is 8 channels
+// (one 16-byte chunk) of one position; consecutive lanes take consecutive positions, so the fp32 reads and the bf16
+// chunk-major writes of a warp are contiguous runs.  The group is read once and kept in registers for the mean, the
+// centred variance and the output pass.
+template <int MAXV>
+__global__ void __launch_bounds__(256) gn2_kernel(Gn2Args a) {
+  __shared__ float part[8][4][48];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  const int cq = a.C / 64;                 // 16-byte chunks per group
+  const int items = cq * a.L, cnt = items * 8;
+  float x[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int j = lane + 32 * k;
+    if (j < items) {
+      const int c = j / a.L, l = j - c * a.L;
+      const int chunk = grp * cq + c;
+      const int64_t row = b * a.L + l;
+      const float4 v0 = *reinterpret_cast<const float4*>(a.in + ((int64_t)(2 * chunk) * a.in_rows + row) * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(a.in + ((int64_t)(2 * chunk + 1) * a.in_rows + row) * 4);
+      x[k][0] = v0.x; x[k][1] = v0.y; x[k][2] = v0.z; x[k][3] = v0.w;
+      x[k][4] = v1.x; x[k][5] = v1.y; x[k][6] = v1.z; x[k][7] = v1.w;
+      s += ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[k][e] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)cnt;
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    if (lane + 32 * k < items) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = x[k][e] - mean; v = fmaf(d, d, v); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / (float)cnt + 1e-5f);
+  const int Lp = a.L + 2;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int j = lane + 32 * k;
+    if (j >= items) continue;
+    const int c = j / a.L, l = j - c * a.L;
+    const int chunk = grp * cq + c, ch = chunk * 8;
+    const int64_t row = b * a.L + l;
+    float y[8];
+    {
+      const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + ch), g1 = *reinterpret_cast<const float4*>(a.gamma + ch + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(a.beta + ch), b1 = *reinterpret_cast<const float4*>(a.beta + ch + 4);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = mish((x[k][e] - mean) * rstd * gm[e] + bt[e]);
+    }
+    if (a.film) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = a.film[ch + e] * y[e] + a.film[a.C + ch + e];
+    }
+    if (a.res_mode == 1) {
+      const int64_t off = (int64_t)(a.r_chunk0 + chunk) * a.r_plane + (4 + b * Lp + l) * 16;
+      const uint4 h = *reinterpret_cast<const uint4*>(a.r_hi + off), lw = *reinterpret_cast<const uint4*>(a.r_lo + off);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lv[4] = {lw.x, lw.y, lw.z, lw.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        y[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lv[e] << 16);
+        y[2 * e + 1] += __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lv[e] & 0xFFFF0000u);
+      }
+    } else if (a.res_mode == 2) {
+      const float4 r0 = *reinterpret_cast<const float4*>(a.r_f32 + ((int64_t)(2 * chunk) * a.in_rows + row) * 4);
+      const float4 r1 = *reinterpret_cast<const float4*>(a.r_f32 + ((int64_t)(2 * chunk + 1) * a.in_rows + row) * 4);
+      y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w; y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+    } else if (a.res_mode == 3) {
+      const float xin = a.r_x[row];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] += fmaf(a.r_w[ch + e], xin, a.r_b[ch + e]);
+    }
+    if (a.out_mode == 2) {
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(y[e], a.p_w[ch + e], d);
+      part[grp][c][l] = d;
+    } else {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * e], y[2 * e + 1]);
+        hi[e] = *reinterpret_cast<uint32_t*>(&h);
+        const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xFFFF0000u);
+        __nv_bfloat162 lw = __floats2bfloat162_rn(y[2 * e] - h0, y[2 * e + 1] - h1);
+        lo[e] = *reinterpret_cast<uint32_t*>(&lw);
+      }
+      int64_t off;
+      if (a.out_mode == 0) off = (int64_t)(a.o_chunk0 + chunk) * a.o_plane + (4 + b * Lp + l) * 16;
+      else off = (int64_t)(a.o_chunk0 + (l & 1) * (a.C / 8) + chunk) * a.o_plane + (4 + b * (a.L / 2 + 2) + (l >> 1)) * 16;
+      *reinterpret_cast<uint4*>(a.o_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(a.o_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  if (a.out_mode == 2) {      // final_conv.1 (Conv1d(128,1,1)): fixed-order sum over groups and chunks -> deterministic
+    __syncthreads();
+    const int l = threadIdx.x;
+    if (l < a.L) {
+      float d = a.p_b[0];
+      for (int g = 0; g < 8; ++g)
+        for (int c = 0; c < cq; ++c) d += part[g][c][l];
+      a.eps[b * a.L + l] = d;
+    }
+  }
+}
+
+int launch_gn2(const Gn2Args& a, cudaStream_t s) {
+  const int items = (a.C / 64) * a.L;
+  if (a.C % 64 != 0 || a.C / 64 > 4 || a.L > 48 || items > 96) {
+    set_error("GroupNorm of %d channels x %d positions is larger than supported (P <= 48)", a.C, a.L);
+    return DGDM_EUNSUPPORTED;
+  }
+  if (items <= 32) gn2_kernel<1><<<(unsigned)a.n, 256, 0, s>>>(a);
+  else gn2_kernel<3><<<(unsigned)a.n, 256, 0, s>>>(a);
+  DGDM_LAUNCH_CHECK();
+  return DGDM_OK;
+}
+
+struct TcBufs {
+  ActBuf f1, hf;                  // full resolution, 128 channels
+  ActBuf eo, p, hh, q, cat;       // half resolution: 256 (even|odd of 128), 128, 256, 256, 512 channels
+  float *t0, *t1, *r;             // fp32 quad-major conv outputs
+  float* film[8];
+};
+
+size_t tc_bufs_bytes(int64_t n, int L) {
+  const int64_t rf = act_rows(n, L), rh = act_rows(n, L / 2);
+  const size_t bf = (size_t)2 * 16 * rf * 16 * 2 + (size_t)(32 + 16 + 32 + 32 + 64) * rh * 16 * 2;
+  return bf + 3 * align_up((size_t)n * L * 128 * sizeof(float), 256) + 64 * 256;
+}
+
+struct TcRun {
+  const dgdm_unet_weights* w; const uint8_t* img; TcPlan pl; int x3; int* err; cudaStream_t s; int64_t n;
+};
+
+// conv over a chunk-major buffer -> fp32 quad-major (for GroupNorm)
+int conv_to_f32(const TcRun& R, const ActBuf& in, int chunk0, int cin, int taps, int roff0, size_t img_off, const float* bias,
+                int cout, int L, float* out) {
+  ConvTcParams P{};
+  P.a_hi = in.hi; P.a_lo = in.lo; P.a_plane = in.plane; P.wimg = R.img + img_off; P.bias = bias; P.N = cout; P.x3 = R.x3;
+  conv_tc_blocks(P, chunk0, cin, taps, roff0);
+  P.n = R.n; P.Ld = L; P.out_mode = 0; P.o_f32 = out; P.o_rows = R.n * L; P.Lo = L; P.o_step = 1; P.o_off = 0; P.err = R.err;
+  return conv_tc_launch(P, R.s);
+}
+
+// One ConditionalResidualBlock1D (diffusion_utils.py:100-120) on the tensor-core path.
+//   in/out: chunk-major buffers (+ first chunk); out_mode 1 splits even/odd positions for the strided conv that follows
+int res_block_tc(const TcRun& R, const TcBufs& B, int bi, const ActBuf& in, int in_chunk0, const ActBuf& h, const ActBuf& out,
+                 int out_chunk0, int out_mode, int L, const float* x_in) {
+  const dgdm_unet_resblock& w = R.w->blocks[bi];
+  const int ci = w.cin, co = w.cout;
+  if (ci == 1) {
+    conv_in_kernel<<<nblk(R.n * L * (co / 4), 256), 256, 0, R.s>>>(B.t0, x_in, w.conv0_w, w.conv0_b, R.n, L, co);
+    DGDM_LAUNCH_CHECK();
+  } else {
+    DGDM_TRY(conv_to_f32(R, in, in_chunk0, ci, 5, 0, R.pl.conv0[bi], w.conv0_b, co, L, B.t0));
+  }
+  Gn2Args g0{};
+  g0.in = B.t0; g0.in_rows = R.n * L; g0.gamma = w.gn0_w; g0.beta = w.gn0_b; g0.film = B.film[bi]; g0.n = R.n; g0.L = L; g0.C = co;
+  g0.res_mode = 0; g0.out_mode = 0; g0.o_hi = h.hi; g0.o_lo = h.lo; g0.o_plane = h.plane; g0.o_chunk0 = 0;
+  DGDM_TRY(launch_gn2(g0, R.s));
+  DGDM_TRY(conv_to_f32(R, h, 0, co, 5, 0, R.pl.conv1[bi], w.conv1_b, co, L, B.t1));
+  Gn2Args g1{};
+  g1.in = B.t1; g1.in_rows = R.n * L; g1.gamma = w.gn1_w; g1.beta = w.gn1_b; g1.film = nullptr; g1.n = R.n; g1.L = L; g1.C = co;
+  if (ci == 1) {
+    g1.res_mode = 3; g1.r_x = x_in; g1.r_w = w.res_w; g1.r_b = w.res_b;
+  } else if (w.res_w) {
+    DGDM_TRY(conv_to_f32(R, in, in_chunk0, ci, 1, 2, R.pl.res[bi], w.res_b, co, L, B.r));
+    g1.res_mode = 2; g1.r_f32 = B.r;
+  } else {
+    g1.res_mode = 1; g1.r_hi = in.hi; g1.r_lo = in.lo; g1.r_plane = in.plane; g1.r_chunk0 = in_chunk0;
+  }
+  g1.out_mode = out_mode; g1.o_hi = out.hi; g1.o_lo = out.lo; g1.o_plane = out.plane; g1.o_chunk0 = out_chunk0;
+  DGDM_TRY(launch_gn2(g1, R.s));
+  return DGDM_OK;
+}
+
+int unet_forward_tc(const dgdm_unet_weights* w, const float* x, int64_t n, int P, int t, float* eps, void* workspace,
+                    size_t workspace_bytes, int precision, cudaStream_t s) {
+  const int L = P, L2 = P / 2;
+  const int64_t nc = n < CHUNK ? n : CHUNK;
+  const int64_t rf = act_rows(nc, L), rh = act_rows(nc, L2);
+  Arena ar(workspace, workspace_bytes);
+  TcBufs B{};
+  const size_t bf16_bytes = (size_t)2 * 16 * rf * 16 * 2 + (size_t)(32 + 16 + 32 + 32 + 64) * rh * 16 * 2;
+  uint8_t* bf = ar.take<uint8_t>(bf16_bytes);
+  B.t0 = ar.take<float>((size_t)nc * L * 128); B.t1 = ar.take<float>((size_t)nc * L * 128); B.r = ar.take<float>((size_t)nc * L * 128);
+  for (int b = 0; b < 8; ++b) B.film[b] = ar.take<float>(2 * 512);
+  int* tc_err = ar.take<int>(1);
+  if (!ar.ok) { set_error("dgdm_unet1d_forward: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
+  {
+    uint8_t* p = bf;
+    auto mk = [&](int chunks, int64_t rows) {
+      ActBuf a; a.plane = rows * 16; a.hi = p; p += (size_t)chunks * a.plane; a.lo = p; p += (size_t)chunks * a.plane; return a;
+    };
+    B.f1 = mk(16, rf); B.hf = mk(16, rf);
+    B.eo = mk(32, rh); B.p = mk(16, rh); B.hh = mk(32, rh); B.q = mk(32, rh); B.cat = mk(64, rh);
+  }
+  DGDM_CHECK_ARG(w->tc_image, "dgdm_unet1d_forward: tensor-core precision needs weights->tc_image (dgdm_unet_pack_tc)");
+  TcRun R{w, (const uint8_t*)w->tc_image, make_tc_plan(w), precision == DGDM_PREC_BF16X3, tc_err, s, 0};
+  DGDM_CUDA(cudaMemsetAsync(tc_err, 0, sizeof(int), s));
+  FilmArgs fa{w->se_w0, w->se_b0, w->se_w1, w->se_b1, {}, {}, {}, {}};
+  for (int b = 0; b < 8; ++b) {
+    fa.film_w[b] = w->blocks[b].film_w; fa.film_b[b] = w->blocks[b].film_b; fa.cout[b] = w->blocks[b].cout;
+    fa.film[b] = B.film[b];
+  }
+  film_kernel<<<8, 256, 0, s>>>(fa, (float)t);
+  DGDM_LAUNCH_CHECK();
+  // rows between samples must be zero; kernels only ever write live rows, so once per call is enough
+  DGDM_CUDA(cudaMemsetAsync(bf, 0, bf16_bytes, s));
+
+  for (int64_t n0 = 0; n0 < n; n0 += nc) {
+    const int64_t m = n - n0 < nc ? n - n0 : nc;
+    R.n = m;
+    const float* xin = x + n0 * L;
+    // down level 0 @L: Res(1->128), Res(128->128) [-> even/odd halves], Downsample1d
+    DGDM_TRY(res_block_tc(R, B, 0, B.f1, 0, B.hf, B.f1, 0, 0, L, xin));
+    DGDM_TRY(res_block_tc(R, B, 1, B.f1, 0, B.hf, B.eo, 0, 1, L, nullptr));
+    {  // Conv1d(128,128,3,stride 2,pad 1): out[j] = w0 in[2j-1] + w1 in[2j] + w2 in[2j+1] = w0 odd[j-1] + w1 even[j] + w2 odd[j]
+      ConvTcParams C{};
+      C.a_hi = B.eo.hi; C.a_lo = B.eo.lo; C.a_plane = B.eo.plane; C.wimg = R.img + R.pl.down; C.bias = w->down_b; C.N = 128; C.x3 = R.x3;
+      C.n_cb = 4;
+      for (int c = 0; c < 2; ++c) {
+        C.cb[c].chunk0 = (uint16_t)(c * 8); C.cb[c].ntap = 1; C.cb[c].tap[0] = ConvTcTap{2, (uint16_t)(1 * 2 + c)};
+        C.cb[2 + c].chunk0 = (uint16_t)(16 + c * 8); C.cb[2 + c].ntap = 2;
+        C.cb[2 + c].tap[0] = ConvTcTap{1, (uint16_t)(0 * 2 + c)};
+        C.cb[2 + c].tap[1] = ConvTcTap{2, (uint16_t)(2 * 2 + c)};
+      }
+      C.n = m; C.Ld = L2; C.out_mode = 1; C.o_hi = B.p.hi; C.o_lo = B.p.lo; C.o_plane = B.p.plane; C.o_chunk0 = 0;
+      C.Lo = L2; C.o_step = 1; C.o_off = 0; C.err = tc_err;
+      DGDM_TRY(conv_tc_launch(C, s));
+    }
+    // down level 1 @L/2: Res(128->256), Res(256->256); its output is the skip => channels 256..511 of cat
+    DGDM_TRY(res_block_tc(R, B, 2, B.p, 0, B.hh, B.q, 0, 0, L2, nullptr));
+    DGDM_TRY(res_block_tc(R, B, 3, B.q, 0, B.hh, B.cat, 32, 0, L2, nullptr));
+    // mid
+    DGDM_TRY(res_block_tc(R, B, 4, B.cat, 32, B.hh, B.q, 0, 0, L2, nullptr));
+    DGDM_TRY(res_block_tc(R, B, 5, B.q, 0, B.hh, B.cat, 0, 0, L2, nullptr));
+    // up level 0 @L/2: cat(x, skip) -> Res(512->128), Res(128->128), Upsample1d
+    DGDM_TRY(res_block_tc(R, B, 6, B.cat, 0, B.hh, B.p, 0, 0, L2, nullptr));
+    DGDM_TRY(res_block_tc(R, B, 7, B.p, 0, B.hh, B.p, 0, 0, L2, nullptr));
+    for (int ph = 0; ph < 2; ++ph) {
+      // ConvTranspose1d(128,128,4,2,1): even t=2m: (k=3, j=m-1), (k=1, j=m); odd t=2m+1: (k=2, j=m), (k=0, j=m+1)
+      ConvTcParams C{};
+      C.a_hi = B.p.hi; C.a_lo = B.p.lo; C.a_plane = B.p.plane; C.wimg = R.img + R.pl.up[ph]; C.bias = w->up_b; C.N = 128; C.x3 = R.x3;
+      conv_tc_blocks(C, 0, 128, 2, ph == 0 ? 1 : 2);
+      C.n = m; C.Ld = L2; C.out_mode = 1; C.o_hi = B.f1.hi; C.o_lo = B.f1.lo; C.o_plane = B.f1.plane; C.o_chunk0 = 0;
+      C.Lo = L; C.o_step = 2; C.o_off = ph; C.err = tc_err;
+      DGDM_TRY(conv_tc_launch(C, s));
+    }
+    // final: Conv1dBlock(128,128,5) then Conv1d(128,1,1) fused into the GroupNorm kernel
+    DGDM_TRY(conv_to_f32(R, B.f1, 0, 128, 5, 0, R.pl.fin, w->fin_b, 128, L, B.t0));
+    Gn2Args gf{};
+    gf.in = B.t0; gf.in_rows = m * L; gf.gamma = w->fin_gn_w; gf.beta = w->fin_gn_b; gf.film = nullptr; gf.n = m; gf.L = L; gf.C = 128;
+    gf.res_mode = 0; gf.out_mode = 2; gf.p_w = w->out_w; gf.p_b = w->out_b; gf.eps = eps + n0 * L;
+    DGDM_TRY(launch_gn2(gf, s));
+  }
+  return DGDM_OK;
+}
+
 }  // namespace
 }  // namespace dgdm
 
@@ -270,7 +589,9 @@ extern "C" size_t dgdm_unet1d_workspace_bytes(int32_t n, int32_t P) {
   using namespace dgdm;
   if (n < 1 || P < 2) return 0;
   int64_t nc = n < CHUNK ? n : CHUNK;
-  return align_up(bufs_floats(nc, P) * sizeof(float), 256) + 8 * align_up(2 * 512 * sizeof(float), 256) + 256 + 4096;
+  const size_t simt = align_up(bufs_floats(nc, P) * sizeof(float), 256);
+  const size_t tc = tc_bufs_bytes(nc, P);
+  return (simt > tc ? simt : tc) + 8 * align_up(2 * 512 * sizeof(float), 256) + 256 + 4096;
 }
 
 extern "C" size_t dgdm_unet_tc_image_bytes(const dgdm_unet_weights* w) {
@@ -312,6 +633,9 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
                    "dgdm_unet1d_forward: block %d is %d->%d, expected %d->%d (train.py:80 configuration)", b,
                    w->blocks[b].cin, w->blocks[b].cout, kCin[b], kCout[b]);
   cudaStream_t s = (cudaStream_t)stream;
+  DGDM_CHECK_ARG(precision == DGDM_PREC_FP32_SIMT || precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_BF16,
+                 "dgdm_unet1d_forward: unknown precision %d", precision);
+  if (precision != DGDM_PREC_FP32_SIMT) return unet_forward_tc(w, x, n, P, t, eps, workspace, workspace_bytes, precision, s);
   const int L = P, L2 = P / 2, R = L + 4, R2 = L2 + 4;
   const int64_t nc = n < CHUNK ? n : CHUNK;
   Arena ar(workspace, workspace_bytes);
