@@ -298,6 +298,14 @@ __global__ void __launch_bounds__(256) conv_in_kernel(float* __restrict__ out, c
   *reinterpret_cast<float4*>(out + idx * 4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// mish for the tensor-core path: ex2.approx + rcp.approx (2^-21-grade, far inside that path's tolerance); the clamp
+// makes x >= 20 return x exactly (n/(n+2) rounds to 1) without a branch and keeps e finite.
+__device__ __forceinline__ float mish_fast(float x) {
+  const float e = __expf(fminf(x, 20.f));
+  const float n = fmaf(e, e, e + e);
+  return x * __fdividef(n, n + 2.f);
+}
+
 struct Gn2Args {
   const float* in; int64_t in_rows;                          // fp32 quad-major [C/4][in_rows][4], row = b*L + l
   const float* gamma; const float* beta; const float* film;  // film: [2C] (scale | shift) or null
@@ -370,7 +378,10 @@ __global__ void __launch_bounds__(256) gn2_kernel(Gn2Args a) {
       const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = mish((x[k][e] - mean) * rstd * gm[e] + bt[e]);
+      for (int e = 0; e < 8; ++e) {
+        const float sc = rstd * gm[e];
+        y[e] = mish_fast(fmaf(x[k][e], sc, fmaf(-mean, sc, bt[e])));
+      }
     }
     if (a.film) {
 #pragma unroll
