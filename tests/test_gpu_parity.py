@@ -178,7 +178,7 @@ def test_unet_golden(g2, g3, precision):
 
 
 @pytest.mark.parametrize("precision", ALL_MODES)
-@pytest.mark.parametrize("n,P", [(1, 14), (300, 14), (4100, 14), (130, 42)])
+@pytest.mark.parametrize("n,P", [(1, 14), (300, 14), (4100, 14), (130, 42), (65, 8), (33, 48), (7, 2)])
 def test_unet_vs_oracle(n, P, g2, precision):
     dm = make2d(precision, torch.from_numpy(g2["objects"]), 2, 1)
     x = syn.initial_noise(n, P, seed=5)
@@ -189,6 +189,21 @@ def test_unet_vs_oracle(n, P, g2, precision):
     # worst single sample, too
     per = (got.cpu() - want).reshape(n, -1).norm(dim=1) / want.reshape(n, -1).norm(dim=1)
     assert float(per.max()) < 10 * UNET_TOL[precision]
+
+
+@pytest.mark.parametrize("precision", TC_MODES)
+@pytest.mark.parametrize("P", [14, 42])
+def test_unet_batch_position_independence(P, g2, precision):
+    """Each sample's denoiser output must not depend on where it sits in the batch: not on its 128-row tile, not on
+    its neighbours across the shared zero rows, not on which 16 384-sample chunk it falls in (n > chunk size
+    exercises the chunk loop).  Bit-exact: the per-sample arithmetic order is fixed."""
+    dm = make2d(precision, torch.from_numpy(g2["objects"]), 2, 1)
+    base = syn.initial_noise(37, P, seed=11).cuda()
+    ref = dm.noise_pred_net(base, 6)
+    n = 16384 + 203 if P == 14 else 1000
+    idx = (torch.arange(n, device="cuda") * 7 + 3) % 37
+    got = dm.noise_pred_net(base[idx].contiguous(), 6)
+    assert torch.equal(got, ref[idx])
 
 
 # ---------------------------------------------------------------------------------------------- K1+K2
