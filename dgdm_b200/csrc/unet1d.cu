@@ -1,5 +1,8 @@
 // K3: ConditionalUnet1D forward (generator/diffusion_utils.py:123-285), configuration of generator/train.py:80.
 //
+// Two implementations behind dgdm_unet1d_forward: the tensor-core path (second half of this file + conv_tc.cu) for
+// DGDM_PREC_BF16X3 / DGDM_PREC_BF16, and the exact fp32 CUDA-core path described next (DGDM_PREC_FP32_SIMT).
+//
 // Activations live channels-last in zero-padded buffers [n][L+4][C] (2 zero rows either side), so a
 // Conv1d(k=5, pad=2) is an implicit GEMM whose A row for (sample b, position l) is the 5*C contiguous
 // floats starting at row l of the padded sample: no im2col is ever materialised.  The strided
@@ -17,9 +20,7 @@
 namespace dgdm {
 // gemm_tc.cu
 size_t gemm_tc_image_bytes(int N, int K);
-bool gemm_tc_eligible(const GemmArgs& g);
 int gemm_tc_pack(const float* W, int N, int K, void* image, cudaStream_t s);
-int gemm_tc(const GemmArgs& g, const void* wimg, int x3, int* err, cudaStream_t s);
 
 namespace {
 
@@ -182,11 +183,9 @@ inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); 
 // Implicit-GEMM conv over padded channels-last buffers.
 //   out[b][PADL + l*o_step + o_off][co] = bias[co] + sum_{tap,ci} w[co][tap][ci] * in[b][l*i_step + i_off + tap][ci]
 // l in [0, Lout); in has Lin+4 rows of ldi floats, out has Lo+4 rows of ldo floats.
-struct TcCtx { const uint8_t* img; int x3; int* err; };   // img == nullptr: CUDA-core path
-
 int conv_gemm(const float* in, int ldi, int Lin_rows, int cin, int taps, int i_step, int i_off, const float* wgt,
               const float* bias, float* out, int ldo, int Lo_rows, int cout, int o_step, int o_off, int64_t n,
-              int Lout, cudaStream_t s, const TcCtx* tc = nullptr, size_t tc_off = 0) {
+              int Lout, cudaStream_t s) {
   GemmArgs g{};
   g.A = in + (int64_t)i_off * ldi; g.W = wgt; g.bias = bias; g.C = out + (int64_t)(PADL + o_off) * ldo;
   g.mask = nullptr; g.add = nullptr;
@@ -195,7 +194,6 @@ int conv_gemm(const float* in, int ldi, int Lin_rows, int cin, int taps, int i_s
   g.c_lr = Lout; g.c_ss = (int64_t)Lo_rows * ldo; g.c_rs = (int64_t)o_step * ldo;
   g.m_lr = g.c_lr; g.m_ss = g.c_ss; g.m_rs = g.c_rs;
   g.act = ACT_NONE;
-  if (tc && tc->img && gemm_tc_eligible(g)) return gemm_tc(g, tc->img + tc_off, tc->x3, tc->err, s);
   return gemm_f32(g, s);
 }
 
@@ -242,22 +240,20 @@ size_t bufs_floats(int64_t n, int L) {
 //   out : padded buffer (ld ldo) receiving cout channels
 //   t0,t1: scratch padded buffers with ld = cout
 int res_block(const dgdm_unet_resblock& w, const float* film, const float* in, int ldi, float* out, int ldo, float* t0,
-              float* t1, int64_t n, int L, cudaStream_t s, const TcCtx* tc, const TcPlan& pl, int bi) {
+              float* t1, int64_t n, int L, cudaStream_t s) {
   const int rows = L + 2 * PADL;
   const int ci = w.cin, co = w.cout;
   // block 0: conv5 -> GN -> Mish -> FiLM
   // (Cin = 1 for the very first conv: K = 5 scalars per row, CUDA-core path)
-  DGDM_TRY(conv_gemm(in, ldi, rows, ci, 5, 1, 0, w.conv0_w, w.conv0_b, t0, co, rows, co, 1, 0, n, L, s,
-                     pl.conv0[bi] == (size_t)-1 ? nullptr : tc, pl.conv0[bi]));
+  DGDM_TRY(conv_gemm(in, ldi, rows, ci, 5, 1, 0, w.conv0_w, w.conv0_b, t0, co, rows, co, 1, 0, n, L, s));
   GnArgs g0{t0, t0, nullptr, w.gn0_w, w.gn0_b, film, n, L, co, co, co, 0};
   DGDM_TRY(launch_gn(g0, s));
   // block 1: conv5 -> GN -> Mish, + residual
-  DGDM_TRY(conv_gemm(t0, co, rows, co, 5, 1, 0, w.conv1_w, w.conv1_b, t1, co, rows, co, 1, 0, n, L, s, tc, pl.conv1[bi]));
+  DGDM_TRY(conv_gemm(t0, co, rows, co, 5, 1, 0, w.conv1_w, w.conv1_b, t1, co, rows, co, 1, 0, n, L, s));
   const float* res = in;
   int ldr = ldi;
   if (w.res_w) {   // 1x1 residual conv when cin != cout; reuse t0 (block-0 output is dead after conv1)
-    DGDM_TRY(conv_gemm(in, ldi, rows, ci, 1, 1, PADL, w.res_w, w.res_b, t0, co, rows, co, 1, 0, n, L, s,
-                       pl.res[bi] == (size_t)-1 ? nullptr : tc, pl.res[bi]));
+    DGDM_TRY(conv_gemm(in, ldi, rows, ci, 1, 1, PADL, w.res_w, w.res_b, t0, co, rows, co, 1, 0, n, L, s));
     res = t0;
     ldr = co;
   }
@@ -653,7 +649,6 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
   Bufs B{};
   float* big = ar.take<float>(bufs_floats(nc, L));
   for (int b = 0; b < 8; ++b) B.film[b] = ar.take<float>(2 * 512);
-  int* tc_err = ar.take<int>(1);
   if (!ar.ok) { set_error("dgdm_unet1d_forward: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
   {
     float* p = big;
@@ -663,14 +658,6 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
     B.q = p; p += (size_t)nc * R2 * 256; B.r = p; p += (size_t)nc * R2 * 256; B.u = p; p += (size_t)nc * R2 * 256;
     B.cat = p;
   }
-  DGDM_CHECK_ARG(precision == DGDM_PREC_FP32_SIMT || precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_BF16,
-                 "dgdm_unet1d_forward: unknown precision %d", precision);
-  DGDM_CHECK_ARG(precision == DGDM_PREC_FP32_SIMT || w->tc_image, "dgdm_unet1d_forward: tensor-core precision needs "
-                 "weights->tc_image (dgdm_unet_pack_tc)");
-  const TcPlan pl = make_tc_plan(w);
-  TcCtx tcc{precision == DGDM_PREC_FP32_SIMT ? nullptr : (const uint8_t*)w->tc_image, precision == DGDM_PREC_BF16X3, tc_err};
-  const TcCtx* tc = &tcc;
-  if (tcc.img) DGDM_CUDA(cudaMemsetAsync(tc_err, 0, sizeof(int), s));
   // FiLM vectors for all 8 blocks, once per call
   FilmArgs fa{w->se_w0, w->se_b0, w->se_w1, w->se_b1, {}, {}, {}, {}};
   for (int b = 0; b < 8; ++b) {
@@ -687,26 +674,26 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
     load_input_kernel<<<nblk(m * L, 256), 256, 0, s>>>(B.x0, x + n0 * L, m, L);
     DGDM_LAUNCH_CHECK();
     // down level 0 @L: Res(1->128), Res(128->128), Downsample
-    DGDM_TRY(res_block(w->blocks[0], B.film[0], B.x0, 1, B.a, 128, B.b, B.c, m, L, s, tc, pl, 0));
-    DGDM_TRY(res_block(w->blocks[1], B.film[1], B.a, 128, B.a, 128, B.b, B.c, m, L, s, tc, pl, 1));
+    DGDM_TRY(res_block(w->blocks[0], B.film[0], B.x0, 1, B.a, 128, B.b, B.c, m, L, s));
+    DGDM_TRY(res_block(w->blocks[1], B.film[1], B.a, 128, B.a, 128, B.b, B.c, m, L, s));
     //   Conv1d(128,128,3,stride 2,pad 1): out[j] = sum_tap in[2j - 1 + tap]  -> padded row 2j + 1 + tap
-    DGDM_TRY(conv_gemm(B.a, 128, R, 128, 3, 2, PADL - 1, w->down_w, w->down_b, B.p, 128, R2, 128, 1, 0, m, L2, s, tc, pl.down));
+    DGDM_TRY(conv_gemm(B.a, 128, R, 128, 3, 2, PADL - 1, w->down_w, w->down_b, B.p, 128, R2, 128, 1, 0, m, L2, s));
     // down level 1 @L/2: Res(128->256), Res(256->256); its output is the skip => second half of cat
-    DGDM_TRY(res_block(w->blocks[2], B.film[2], B.p, 128, B.q, 256, B.r, B.u, m, L2, s, tc, pl, 2));
-    DGDM_TRY(res_block(w->blocks[3], B.film[3], B.q, 256, B.cat + 256, 512, B.r, B.u, m, L2, s, tc, pl, 3));
+    DGDM_TRY(res_block(w->blocks[2], B.film[2], B.p, 128, B.q, 256, B.r, B.u, m, L2, s));
+    DGDM_TRY(res_block(w->blocks[3], B.film[3], B.q, 256, B.cat + 256, 512, B.r, B.u, m, L2, s));
     // mid @L/2
-    DGDM_TRY(res_block(w->blocks[4], B.film[4], B.cat + 256, 512, B.q, 256, B.r, B.u, m, L2, s, tc, pl, 4));
-    DGDM_TRY(res_block(w->blocks[5], B.film[5], B.q, 256, B.cat, 512, B.r, B.u, m, L2, s, tc, pl, 5));
+    DGDM_TRY(res_block(w->blocks[4], B.film[4], B.cat + 256, 512, B.q, 256, B.r, B.u, m, L2, s));
+    DGDM_TRY(res_block(w->blocks[5], B.film[5], B.q, 256, B.cat, 512, B.r, B.u, m, L2, s));
     // up level 0 @L/2: cat(x, skip) -> Res(512->128), Res(128->128), Upsample
-    DGDM_TRY(res_block(w->blocks[6], B.film[6], B.cat, 512, B.p, 128, B.ta, B.tb, m, L2, s, tc, pl, 6));
-    DGDM_TRY(res_block(w->blocks[7], B.film[7], B.p, 128, B.p, 128, B.ta, B.tb, m, L2, s, tc, pl, 7));
+    DGDM_TRY(res_block(w->blocks[6], B.film[6], B.cat, 512, B.p, 128, B.ta, B.tb, m, L2, s));
+    DGDM_TRY(res_block(w->blocks[7], B.film[7], B.p, 128, B.p, 128, B.ta, B.tb, m, L2, s));
     //   ConvTranspose1d(128,128,4,stride 2,pad 1): out[t] = sum_{j,k: t = 2j - 1 + k} in[j] w[k]
     //   even t=2m: taps (k=3, j=m-1), (k=1, j=m); odd t=2m+1: taps (k=2, j=m), (k=0, j=m+1).
     //   up_w is packed [phase][cout][2][cin] (even: k=3,1; odd: k=2,0) so each phase is a 2-tap conv.
-    DGDM_TRY(conv_gemm(B.p, 128, R2, 128, 2, 1, PADL - 1, w->up_w, w->up_b, B.a, 128, R, 128, 2, 0, m, L2, s, tc, pl.up[0]));
-    DGDM_TRY(conv_gemm(B.p, 128, R2, 128, 2, 1, PADL, w->up_w + 128 * 2 * 128, w->up_b, B.a, 128, R, 128, 2, 1, m, L2, s, tc, pl.up[1]));
+    DGDM_TRY(conv_gemm(B.p, 128, R2, 128, 2, 1, PADL - 1, w->up_w, w->up_b, B.a, 128, R, 128, 2, 0, m, L2, s));
+    DGDM_TRY(conv_gemm(B.p, 128, R2, 128, 2, 1, PADL, w->up_w + 128 * 2 * 128, w->up_b, B.a, 128, R, 128, 2, 1, m, L2, s));
     // final: Conv1dBlock(128,128,5) then Conv1d(128,1,1)
-    DGDM_TRY(conv_gemm(B.a, 128, R, 128, 5, 1, 0, w->fin_w, w->fin_b, B.b, 128, R, 128, 1, 0, m, L, s, tc, pl.fin));
+    DGDM_TRY(conv_gemm(B.a, 128, R, 128, 5, 1, 0, w->fin_w, w->fin_b, B.b, 128, R, 128, 1, 0, m, L, s));
     GnArgs gf{B.b, B.b, nullptr, w->fin_gn_w, w->fin_gn_b, nullptr, m, L, 128, 128, 128, 0};
     DGDM_TRY(launch_gn(gf, s));
     out_proj_kernel<<<nblk(m * L * 32, 256), 256, 0, s>>>(eps + n0 * L, B.b, w->out_w, w->out_b, m, L, 128);
