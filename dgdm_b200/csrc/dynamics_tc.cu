@@ -21,7 +21,7 @@
 //            sign bits, convert to bf16 (hi [+ lo]) and tcgen05.st it back as the next layer's A operand.
 //            The last backward layer is reduced over the tile's rows per pair with warp shuffles and written
 //            to a per-(pair,tile) slot; a small second kernel adds the slots in fixed order (deterministic).
-// TMEM: two 256-column regions that swap roles every layer (A operand, per 64-wide k-block [hi 32 | lo 32] columns,
+// TMEM: two 256-column regions that swap roles every layer (A operand, per 16-feature group [hi 8 | lo 8] columns,
 // and fp32 accumulator); the epilogue rewrites the accumulator in place into the next A operand.
 //
 // Precision modes: BF16X3 splits both operands into bf16 hi + lo and issues 3 MMAs (hi*hi, lo*hi, hi*lo) into
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
   } else if (warp == NEPI + 1) {
     // =============================== MMA issuer ===============================
     // TMEM is two 256-column regions.  During a segment the A operand lives in region `cur` (per 64-wide
-    // k-block kb: hi at [64kb, 64kb+32), lo at [64kb+32, 64kb+64)) and the accumulator in the other one.
+    // K=16 step ks of k-block kb: hi at [64kb+16ks, +8), lo at [64kb+16ks+8, +8)) and the accumulator in the other one.
     // The epilogue converts the accumulator IN PLACE into the next layer's A operand, k-block by k-block,
     // and hands each k-block over on its own mbarrier, so the next layer's MMAs start after a quarter of the
     // epilogue instead of all of it; the roles of the two regions then swap.
@@ -355,10 +355,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 #pragma unroll
             for (int ks = 0; ks < KBLK / 16; ++ks) {
               const uint64_t bdesc = make_b_desc(b_addr + ks * 32);
-              const uint32_t a_col = (uint32_t)(kb * 64 + ks * 8);             // 16 bf16 = 8 TMEM columns
+              const uint32_t a_col = (uint32_t)(kb * 64 + ks * 16);            // 16 bf16 = 8 TMEM columns: [hi 8 | lo 8]
               tc_mma_ts(d_base, a_base + a_col, bdesc, idesc, accum);
               accum = 1;
-              if (X3 && part == 0) tc_mma_ts(d_base, a_base + a_col + 32, bdesc, idesc, 1);
+              if (X3 && part == 0) tc_mma_ts(d_base, a_base + a_col + 8, bdesc, idesc, 1);
             }
             tc_commit(&S.empty[stage]);           // stage reusable once these MMAs have read it
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -373,9 +373,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
     // =============================== epilogue warps 0..15 ===============================
     // warp (q, hq): TMEM lane quadrant q (rows 32q..32q+31); of every 64-feature k-block it owns the 16 features
     // [16hq, 16hq+16).  Four warps per scheduler keep the issue slots busy while a sibling waits on a TMEM load, a
-    // named barrier or tcgen05.wait::st (with two lock-stepped warps per scheduler the epilogue was latency-bound
-    // at ~1100 cycles per k-block).  The four warps of a quadrant share lanes, so they meet on a 128-thread named
-    // barrier before overwriting accumulator columns a sibling still has to read.
+    // tcgen05.wait::st (with two lock-stepped warps per scheduler the epilogue was latency-bound at ~1100 cycles per
+    // k-block).  A warp rewrites exactly the 16 accumulator columns it read ([hi 8 | lo 8] of the same features), so
+    // the four warps of a quadrant never wait for each other in the layer loop.
     const int q = warp & 3, hq = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
@@ -410,9 +410,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
       };
       // store 16 features (k-block kb, group hq) of this row as bf16 hi [+ lo] into region `reg`
       auto store_packed = [&](uint32_t reg, int kb, const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
-        const uint32_t col = reg * 256u + (uint32_t)(kb * 64 + hq * 8);
+        // the 16 accumulator columns this warp read become [hi 8 | lo 8] of the same 16 features: no other warp's
+        // columns are touched, so the in-place rewrite needs no barrier between the warps of a lane quadrant
+        const uint32_t col = reg * 256u + (uint32_t)(kb * 64 + hq * 16);
         tmem_st8(lane_addr + col, hi);
-        if (X3) tmem_st8(lane_addr + col + 32, lo);
+        if (X3) tmem_st8(lane_addr + col + 8, lo);
       };
       auto store_a = [&](uint32_t reg, int kb, const float (&v)[16]) {
         uint32_t hi[8], lo[8];
@@ -473,7 +475,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           for (int kb = 0; kb < 4; ++kb) {
             tmem_ld_wait16(rr[kb & 1]);
             if (kb + 1 < 4) tmem_ld16_async(d_addr + (uint32_t)((kb + 1) * 64 + hq * 16), rr[(kb + 1) & 1]);
-            quad_sync();                            // all four 16-feature groups of k-block kb are now in registers
             if (sgm.kind == K_FWD) {
               const float4* b4 = reinterpret_cast<const float4*>(&S.bias[sgm.layer - 1][kb * 64 + hq * 16]);
               float z[16];
