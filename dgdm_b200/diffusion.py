@@ -170,6 +170,8 @@ class Diffusion:
         self.std = torch.tensor(std)
         self.threshold_std = self.threshold / self.std
         self._ws: Dict[str, torch.Tensor] = {}
+        self._graphs: Dict[tuple, tuple] = {}                    # captured passes (guided_sample(cuda_graph=True))
+        self._obj_version = 0                                    # bumped by set_objects: captured graphs read its buffers
         self.object_vertices = None
         self.fps_starts = None
         self._obj_dev: Optional[torch.Tensor] = None
@@ -216,6 +218,8 @@ class Diffusion:
         self.object_vertices = object_vertices
         self.fps_starts = fps_starts
         self._obj_dev = self.encode_objects(object_vertices, fps_starts)
+        self._obj_version += 1                                   # graphs captured against the old object codes are stale
+        self._graphs.clear()
 
     # ------------------------------------------------------------------------------------------
     def noise_pred_net(self, sample: torch.Tensor, timesteps) -> torch.Tensor:
@@ -406,6 +410,27 @@ class Diffusion:
             return SCALE_2D_CONV if conv else SCALE_2D
         return SCALE_3D_CONV if conv else SCALE_3D
 
+    def _graphed(self, key, noise: torch.Tensor, batch_size: int, body) -> Dict[str, torch.Tensor]:
+        """Run ``body(noise)`` through a CUDA graph captured once per ``key``.  The first call runs the body eagerly
+        (which sizes every cached workspace and performs the library's one-time kernel-attribute setup), then captures
+        it on a side stream with a static copy of the noise; later calls copy the new noise in and replay.  Outputs
+        are cloned so they survive the next replay."""
+        nz = self._check_noise(noise, batch_size)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = nz.clone()
+            body(static_in)                                      # eager warm-up
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = body(static_in)
+            ent = (g, static_in, static_out, dict(self._ws))     # keep the captured workspaces alive if the cache regrows
+            self._graphs[key] = ent
+        g, static_in, static_out = ent[:3]
+        static_in.copy_(nz)
+        g.replay()
+        return {k: v.clone() for k, v in static_out.items()}
+
     def _check_noise(self, noise: torch.Tensor, batch_size: int) -> torch.Tensor:
         if noise.shape[0] != batch_size or noise.shape[1] != self.num_points:
             raise ValueError(f"noise must be ({batch_size},{self.num_points},1), got {tuple(noise.shape)}")
@@ -452,11 +477,19 @@ class Diffusion:
         return objs, M.get_best_ids_all_metrics(objs, opt_obj)
 
     def guided_sample(self, batch_idx, batch_size, noise, save_dir=None, opt_obj="rotate", ori_range=[-1.0, 1.0],
-                      unguided_sample=None, top_k: int = 1, trace: Optional[list] = None):
+                      unguided_sample=None, top_k: int = 1, trace: Optional[list] = None, cuda_graph: bool = False):
         """Per-object guided sampling (diffusion.py:541-576): every object restarts from the same ``noise``.
-        Returns {'designs' (n_obj,B,P,1), 'scores' (n_obj,B), 'best_ids' (n_obj,top_k), 'best_scores'}."""
+        Returns {'designs' (n_obj,B,P,1), 'scores' (n_obj,B), 'best_ids' (n_obj,top_k), 'best_scores'}.
+
+        ``cuda_graph=True`` captures the whole pass (every denoiser forward, guidance step, DDIM update, the scoring
+        pass and the selection: a few hundred launches) into one CUDA graph on first use and replays it afterwards;
+        results are bit-identical to the eager path.  It pays when the pass is launch-bound (small batches)."""
         if opt_obj not in OBJECTIVES:
             raise ValueError("opt obj not supported")
+        if cuda_graph and trace is None and opt_obj != "convergence":
+            key = ("per_object", batch_size, self._obj_dev.shape[0], opt_obj, tuple(ori_range), top_k, self._obj_version)
+            return self._graphed(key, noise, batch_size, lambda nz: self.guided_sample(
+                batch_idx, batch_size, nz, save_dir, opt_obj, ori_range, None, top_k))
         n_obj = self._obj_dev.shape[0]
         B, P = batch_size, self.num_points
         scale = self.classifier_scale(opt_obj)
@@ -485,11 +518,17 @@ class Diffusion:
         return {"designs": x.reshape(n_obj, B, P, 1), "scores": scores, "best_ids": idx, "best_scores": best}
 
     def guided_sample_multi_object(self, batch_idx, batch_size, noise, save_dir=None, opt_obj="rotate",
-                                   ori_range=[-1.0, 1.0], top_k: int = 1, trace: Optional[list] = None):
+                                   ori_range=[-1.0, 1.0], top_k: int = 1, trace: Optional[list] = None,
+                                   cuda_graph: bool = False):
         """One trajectory guided by the object-averaged gradient (diffusion.py:621-647).
-        Returns {'designs' (B,P,1), 'scores' (B,) mean over objects, 'best_ids' (top_k,), 'best_scores'}."""
+        Returns {'designs' (B,P,1), 'scores' (B,) mean over objects, 'best_ids' (top_k,), 'best_scores'}.
+        ``cuda_graph``: as in :meth:`guided_sample`."""
         if opt_obj not in OBJECTIVES or opt_obj == "convergence":
             raise ValueError("opt obj not supported")
+        if cuda_graph and trace is None:
+            key = ("multi_object", batch_size, self._obj_dev.shape[0], opt_obj, tuple(ori_range), top_k, self._obj_version)
+            return self._graphed(key, noise, batch_size, lambda nz: self.guided_sample_multi_object(
+                batch_idx, batch_size, nz, save_dir, opt_obj, ori_range, top_k))
         n_obj = self._obj_dev.shape[0]
         B, P = batch_size, self.num_points
         scale = self.classifier_scale(opt_obj, multi=True)

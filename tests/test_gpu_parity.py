@@ -370,6 +370,30 @@ def test_guided_loop_3d_golden(g3, precision):
         grad_close(rec["grad"][0], g3[f"loop_grad_s{i}"], tol_for(precision, 12), f"3d loop s{i}")
 
 
+@pytest.mark.parametrize("precision", TC_MODES)
+def test_cuda_graph_replay_matches_eager(g2, precision):
+    """guided_sample(cuda_graph=True): the captured pass replays bit-identically to the eager path, for new noise
+    too, in both sampler modes; set_objects invalidates captured graphs."""
+    objs = torch.from_numpy(g2["objects"])
+    dm = make2d(precision, objs, 6, 2)
+    B = 16
+    for seed in (0, 1, 2):
+        noise = syn.initial_noise(B, 14, seed=seed).cuda()
+        for fn in (dm.guided_sample, dm.guided_sample_multi_object):
+            want = fn(0, B, noise, opt_obj="rotate_clockwise", top_k=3)
+            got = fn(0, B, noise, opt_obj="rotate_clockwise", top_k=3, cuda_graph=True)
+            for k in want:
+                assert torch.equal(got[k], want[k]), (seed, fn.__name__, k)
+    assert len(dm._graphs) == 2
+    dm.set_objects(objs.flip(0))
+    assert len(dm._graphs) == 0
+    noise = syn.initial_noise(B, 14, seed=3).cuda()
+    want = dm.guided_sample(0, B, noise, opt_obj="shift_up")
+    got = dm.guided_sample(0, B, noise, opt_obj="shift_up", cuda_graph=True)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+
+
 # ---------------------------------------------------------------------------------------------- f-1 / f-3
 def test_denoise_from_data_and_predicted_tables(g2):
     objs = torch.from_numpy(g2["objects"])
