@@ -18,7 +18,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libdgdm_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"] + os.environ.get("DGDM_NVCC_EXTRA", "").split()
 
 
 def _newer(src: str, dst: str, extra=()) -> bool:

@@ -279,6 +279,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
+  // All 512 columns are allocated, so the base is column 0 of lane 0.  The MMA issuer relies on that: with literal
+  // TMEM addresses every tcgen05.mma operand is warp-uniform and lives in uniform registers; taking the base from
+  // shared memory made nvcc wrap EVERY mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~100 cycles of issue each,
+  // which starved the tensor pipe between weight tiles).
+  if (tmem != 0u) { if (tid == 0 && P.err) atomicExch(P.err, 9); __trap(); }
 
   const int tiles_mine = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tiles_per_seg = X3 ? 8 : 4;       // weight tiles per segment: 4 k-blocks x (hi [, lo])
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         for (int sg = 0; sg < P.n_seg; ++sg) {
           const Seg sgm = P.seg[sg];
           const uint32_t idesc = make_idesc(sgm.n_rows);
-          const uint32_t a_base = tmem + cur * 256u, d_base = tmem + (cur ^ 1u) * 256u;
+          const uint32_t a_base = cur * 256u, d_base = (cur ^ 1u) * 256u;      // TMEM base is 0 (checked above)
           uint32_t accum = sgm.accum;
           for (int j = 0; j < tiles_per_seg; ++j) {
             const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;

@@ -27,7 +27,11 @@ __global__ void __launch_bounds__(NT, 1) k(int mode, int iters, const uint8_t* s
   __shared__ volatile int done;
   __shared__ uint16_t masks[16][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) ((uint32_t*)buf)[i] = 0;
+  for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;           // (mode & 8): random bf16 pairs in (-2, 2)
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    ((uint32_t*)buf)[i] = (mode & 8) ? ((h & 0x807F807Fu) | 0x3F003F00u) : 0u;
+  }
   if (threadIdx.x == 0) {
     done = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar)));
@@ -43,6 +47,19 @@ __global__ void __launch_bounds__(NT, 1) k(int mode, int iters, const uint8_t* s
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tm = tbase;
+  if ((mode & 8) && warp >= 2 && warp < 6) {                                   // A operand columns 0..63 <- random bf16 pairs
+    uint32_t h = threadIdx.x * 2654435761u + 12345u;
+    for (int c = 0; c < 64; c += 8) {
+      uint32_t r[8];
+      for (int i = 0; i < 8; ++i) { h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; r[i] = (h & 0x807F807Fu) | 0x3F003F00u; }
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                   ::"r"(tm + ((uint32_t)((warp - 2) * 32) << 16) + c), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -111,9 +128,9 @@ int main() {
   uint8_t* src; cudaMalloc(&src, 28 * 32768); cudaMemset(src, 0, 28 * 32768);
   const int smem = 1024 + 5 * 32768;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int iters = 20000;
-  const char* names[8] = {"MMA alone", "+ bulk ring", "+ TMEM ld/st", "+ bulk + TMEM", "", "", "+ TMEM + masks", "+ bulk + TMEM + masks"};
-  for (int mode : {0, 1, 2, 3, 6, 7}) {
+  const int iters = 200000;
+  const char* names[16] = {"MMA alone", "+ bulk ring", "+ TMEM ld/st", "+ bulk + TMEM", "", "", "+ TMEM + masks", "+ bulk + TMEM + masks", "random data: MMA alone", "random: + bulk", "random: + TMEM", "random: + bulk + TMEM", "", "", "", "random: + bulk + TMEM + masks"};
+  for (int mode : {0, 1, 2, 3, 6, 7, 8, 9, 10, 11, 15}) {
     for (int rep = 0; rep < 2; ++rep) { cudaMemset(d, 0, 148 * 4 * 8); k<<<148, NT, smem>>>(mode, iters, src, d); cudaDeviceSynchronize(); }
     long long h[148 * 4]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     double mma = 0, bytes = 0, cyc = 0, tm = 0;
