@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = S.tmem_base;
+  // all 512 columns allocated => base 0; the MMA issuer uses literal addresses so its operands stay warp-uniform
+  if (tmem != 0u) { if (tid == 0 && P.err) atomicExch(P.err, 19); __trap(); }
   const int my_tiles = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp >= 4 && warp < 12) {
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
         const int acc = t & 1;
         bar_wait(&S.d_empty[acc], ((t >> 1) & 1) ^ 1, P.err, 13);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem + (uint32_t)acc * 256u;
+        const uint32_t d = (uint32_t)acc * 256u;
         uint32_t accum = 0;
         for (int kb = 0; kb < P.n_kb; ++kb) {
           bar_wait(&S.full_a[stage], phase, P.err, 14);
