@@ -242,6 +242,16 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
+// Optional in-kernel timeline (build with DGDM_NVCC_EXTRA=-DDGDM_TRUNK_TRACE python -m dgdm_b200.build -f, read with
+// dgdm_trunk_trace_read; scratch/trace2.py prints it): clock64 stamps of CTA 0, third tile, per role.
+// Development tool; compiled out by default.
+#ifdef DGDM_TRUNK_TRACE
+__device__ long long g_trace[8192];
+#define TR(slot) do { if (blockIdx.x == 0 && t == 2) g_trace[slot] = clock64(); } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
+
 struct Smem {
   uint64_t full[NSTAGE], empty[NSTAGE], a_ready[4], d_ready;
   uint32_t tmem_base, pad_;
@@ -300,6 +310,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             // image order inside a segment: kb0.hi, kb0.lo, kb1.hi, kb1.lo, ...
             const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;
             mbar_wait(&S.empty[stage], phase ^ 1, P.err, 1);
+            TR(6144 + sg * 8 + j);
             mbar_arrive_expect_tx(&S.full[stage], tile_bytes);
             bulk_g2s(ring + stage * WTILE_BYTES, P.img + sgm.img_off + (size_t)(kb * 2 + part) * tile_bytes, tile_bytes,
                      &S.full[stage]);
@@ -326,12 +337,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           uint32_t accum = sgm.accum;
           for (int j = 0; j < tiles_per_seg; ++j) {
             const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;
+            TR(sg * 64 + j * 4 + 0);
             if (part == 0) {
               mbar_wait(&S.a_ready[kb], a_phase, P.err, 2);
               tc_fence_after();
             }
+            TR(sg * 64 + j * 4 + 1);
             mbar_wait(&S.full[stage], phase, P.err, 3);
             tc_fence_after();
+            TR(sg * 64 + j * 4 + 2);
             const uint32_t b_addr = smem_u32(ring + stage * WTILE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < KBLK / 16; ++ks) {
@@ -342,6 +356,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
               if (X3 && part == 0) tc_mma_ts(d_base, a_base + a_col + 8, bdesc, idesc, 1);
             }
             tc_commit(&S.empty[stage]);           // stage reusable once these MMAs have read it
+            TR(sg * 64 + j * 4 + 3);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
           tc_commit(&S.d_ready);                  // accumulator complete
@@ -444,6 +459,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         mbar_wait(&S.d_ready, d_phase, P.err, 4);
         d_phase ^= 1;
         tc_fence_after();
+        if (lane == 0 && (warp == 0 || warp == 15)) TR(2048 + (warp == 15 ? 2048 : 0) + sg * 16);
 
         if (sgm.kind == K_MID) {
           build_a1(1, cur);                         // second K-half of a1 replaces the first; accumulator stays
@@ -478,6 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
               store_a(dreg, kb, v);
             }
             signal_kb(kb);
+            if (lane == 0 && (warp == 0 || warp == 15)) TR(2048 + (warp == 15 ? 2048 : 0) + sg * 16 + 1 + kb);
           }
           cur ^= 1;
         } else if (sgm.kind == K_OUT) {
@@ -758,6 +775,12 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
 }
 
 }  // namespace dgdm
+
+#ifdef DGDM_TRUNK_TRACE
+extern "C" int dgdm_trunk_trace_read(long long* out, int32_t n) {
+  return cudaMemcpyFromSymbol(out, dgdm::g_trace, sizeof(long long) * (size_t)(n < 8192 ? n : 8192)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 extern "C" int dgdm_trunk_timing(int32_t enable) {
   dgdm::g_timing.on = enable != 0;

@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests"); sys.path.insert(0, "/root/repo/oracle")
+import os; R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path[:0] = [R, R + "/tests", R + "/oracle"]
 from dgdm_b200 import synthetic as syn
 from test_gpu_parity import make2d
 prec = sys.argv[1]
