@@ -163,8 +163,13 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 
 __device__ __forceinline__ int pair_obj(int64_t p, int opd, int n_designs, int n_obj, const int32_t* pair_object) {
   if (pair_object) return pair_object[p];
-  if (opd == 1) return (int)(p / (n_designs / n_obj));
-  return (int)(p % opd);
+  // 32-bit arithmetic whenever the pair index allows it: this runs on the tile-to-tile critical path and an emulated
+  // 64-bit division costs ~150 cycles
+  if (opd == 1) {
+    const int dpo = n_designs / n_obj;
+    return p <= 0x7fffffffll ? (int)((uint32_t)p / (uint32_t)dpo) : (int)(p / dpo);
+  }
+  return p <= 0x7fffffffll ? (int)((uint32_t)p % (uint32_t)opd) : (int)(p % opd);
 }
 
 // Split 32 fp32 values into packed bf16 hi (and lo = rn(v - hi)) pairs; element 2i in the low half.
@@ -381,20 +386,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 
     for (int t = 0; t < tiles_mine; ++t) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-      const int64_t r_glob = (int64_t)tile * TILE_M + row;
+      // Row -> (pair, pose row) with ONE 64-bit division per tile; everything per row is 32-bit (this code sits on the
+      // tile-to-tile critical path: the timeline showed ~1900 cycles of index arithmetic here with 64-bit divisions).
+      const int64_t base = (int64_t)tile * TILE_M;
+      const int64_t p_first = base / P.G;
+      const uint32_t rem0 = (uint32_t)(base - p_first * P.G), Gu = (uint32_t)P.G;
+      const uint32_t rofs = rem0 + (uint32_t)row, dq = rofs / Gu;          // rofs < G + 128
+      const int64_t r_glob = base + row;
       const bool live = r_glob < P.n_rows;
-      const int64_t pr = live ? r_glob / P.G : -1;
-      const int g = live ? (int)(r_glob % P.G) : 0;
+      const int64_t pr = live ? p_first + dq : -1;
+      const int g = live ? (int)(rofs - dq * Gu) : 0;
       const float coef = (live && P.obj.row_coef) ? P.obj.row_coef[r_glob] : 1.f;
       const float* u_row = nullptr; const float* c_row = nullptr;
       if (live) {
-        u_row = P.U + (pr / P.opd) * P.H1;
+        const int64_t design = P.opd == 1 ? pr : (pr <= 0x7fffffffll ? (int64_t)((uint32_t)pr / (uint32_t)P.opd) : pr / P.opd);
+        u_row = P.U + design * P.H1;
         c_row = P.Cst + (int64_t)pair_obj(pr, P.opd, P.n_designs, P.n_obj, P.pair_object) * P.H1;
       }
-      const int64_t p_first = ((int64_t)tile * TILE_M) / P.G;
-      int64_t last_row = (int64_t)tile * TILE_M + TILE_M - 1;
+      int64_t last_row = base + TILE_M - 1;
       if (last_row >= P.n_rows) last_row = P.n_rows - 1;
-      const int64_t p_last = last_row / P.G;
+      const int64_t p_last = p_first + (rem0 + (uint32_t)(last_row - base)) / Gu;
       uint32_t cur = 0;                            // region holding the A operand of the current segment
 
       // hand k-block kb of the A operand over to the MMA issuer
