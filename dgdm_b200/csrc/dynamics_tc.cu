@@ -429,34 +429,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         store_packed(reg, kb, hi, lo);
       };
       // layer-1 activations for K-half `kh` -> A operand in region `reg` + layer-1 sign bits
+      // z = Cst[obj] + U[design] + V[g] for the 16 features [col0, col0 + 16) of this row.
+      // The pose table is read TRANSPOSED ([H1][G]): lanes are consecutive pose rows g, so each feature is one
+      // coalesced 128-byte request; all loads are issued before use.  U/Cst rows are warp-broadcast loads.
+      auto load_z = [&](int col0, float (&z)[16]) {
+        float pv[16];
+        {
+          const float* vt = P.Vt + (int64_t)col0 * P.G + g;
+          const uint32_t G32 = (uint32_t)P.G;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pv[i] = live ? __ldg(vt + i * G32) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) {
+            float4 k4 = *reinterpret_cast<const float4*>(c_row + col0 + i);
+            float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + i);
+            a.x = (k4.x + u4.x) + pv[i]; a.y = (k4.y + u4.y) + pv[i + 1]; a.z = (k4.z + u4.z) + pv[i + 2]; a.w = (k4.w + u4.w) + pv[i + 3];
+          }
+          z[i] = a.x; z[i + 1] = a.y; z[i + 2] = a.z; z[i + 3] = a.w;
+        }
+      };
+      // The loads of k-block kb+1 are in flight while k-block kb is converted and handed over: an L2 round trip is
+      // ~1300 cycles here, far more than a bf16 k-block of MMAs (512), so without the overlap layer 1 is load-bound.
+      // (Measured: +1.6 % in bf16.  In fp32-grade mode a k-block of MMAs (1536 cycles) already covers the round trip and
+      // the second buffer only costs registers at the 96-register cap, so that mode keeps the plain loop.)
       auto build_a1 = [&](int kh, uint32_t reg) {
+        if constexpr (X3) {
 #pragma unroll 1
+          for (int kb = 0; kb < 4; ++kb) {
+            float z[16];
+            load_z(kh * 256 + kb * 64 + hq * 16, z);
+            uint32_t hi[8], lo[8];
+            S.mask[kh * 16 + kb * 4 + hq][row] = (uint16_t)relu_split16<X3>(z, hi, lo);
+            store_packed(reg, kb, hi, lo);
+            signal_kb(kb);
+          }
+        } else {
+        float zb[2][16];
+        load_z(kh * 256 + hq * 16, zb[0]);
+#pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-          const int col0 = kh * 256 + kb * 64 + hq * 16;
-          float z[16];
-          // The pose table is read TRANSPOSED ([H1][G]): lanes are consecutive pose rows g, so each feature is one
-          // coalesced 128-byte request; all loads are issued before use.  U/Cst rows are warp-broadcast loads.
-          float pv[16];
-          {
-            const float* vt = P.Vt + (int64_t)col0 * P.G + g;
-            const uint32_t G32 = (uint32_t)P.G;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pv[i] = live ? __ldg(vt + i * G32) : 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) {
-              float4 k4 = *reinterpret_cast<const float4*>(c_row + col0 + i);
-              float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + i);
-              a.x = (k4.x + u4.x) + pv[i]; a.y = (k4.y + u4.y) + pv[i + 1]; a.z = (k4.z + u4.z) + pv[i + 2]; a.w = (k4.w + u4.w) + pv[i + 3];
-            }
-            z[i] = a.x; z[i + 1] = a.y; z[i + 2] = a.z; z[i + 3] = a.w;
-          }
+          if (kb + 1 < 4) load_z(kh * 256 + (kb + 1) * 64 + hq * 16, zb[(kb + 1) & 1]);
           uint32_t hi[8], lo[8];
-          S.mask[kh * 16 + kb * 4 + hq][row] = (uint16_t)relu_split16<X3>(z, hi, lo);
+          S.mask[kh * 16 + kb * 4 + hq][row] = (uint16_t)relu_split16<X3>(zb[kb & 1], hi, lo);
           store_packed(reg, kb, hi, lo);
           signal_kb(kb);
+        }
         }
       };
 
