@@ -44,7 +44,11 @@ constexpr int NTHREADS = (NEPI + 2) * 32;      // + producer warp + MMA warp
 constexpr int MAX_SEG = 20;
 constexpr int MASK_WORDS = 16 + 7 * 8;         // layer 1 up to 512 wide + 7 layers of 256
 
-enum { K_FWD = 0, K_MID = 1, K_OUT = 2, K_BWD = 3, K_LAST = 4 };
+// K_OUT: the 3-wide output layer as a 16-column MMA segment (bf16 mode).  K_FOUT (fp32-grade mode): the last hidden
+// layer whose epilogue also evaluates the output layer on CUDA cores and seeds the backward pass -- with three MMAs per
+// product the 16-column segment cost almost a full layer of tensor time plus two hand-off chains (+2.5 % without it);
+// in bf16 mode the segment is cheap and the heavier fused epilogue measured 2 % slower, so both forms exist.
+enum { K_FWD = 0, K_MID = 1, K_OUT = 2, K_BWD = 3, K_LAST = 4, K_FOUT = 5 };
 
 struct Seg {
   uint32_t img_off;    // byte offset of the segment's tiles in the image
@@ -64,6 +68,7 @@ struct TcParams {
   dgdm_objective obj;
   int64_t n_rows;       // n_pairs * G
   int n_tiles, G, H1, opd, n_designs, n_obj, n_seg, x3, backward;
+  int alt;              // 1: an odd number of region swaps per tile -> alternate the start region tile by tile
   Seg seg[MAX_SEG];
 };
 
@@ -265,6 +270,7 @@ struct Smem {
   float b_out[4];
   float red[4][256];            // per lane-quadrant partial column sums
   float red_s[4];
+  float lg[4][TILE_M][3];      // partial logits of the four 16-feature-group warps of a row
   uint16_t mask[2 * MASK_WORDS][TILE_M];      // ReLU sign bits, one halfword per (16-feature group, row)
 };
 
@@ -334,7 +340,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0;
       for (int t = 0; t < tiles_mine; ++t) {
-        uint32_t cur = 0;
+        // fused-output plan: 13 region swaps per backward tile: alternate the start region so that the next tile's layer-1 operand lands in
+        // the region K_LAST's MMAs have finished with, never in the accumulator its epilogue is still reading
+        uint32_t cur = P.alt ? (uint32_t)(t & 1) : 0u;
         for (int sg = 0; sg < P.n_seg; ++sg) {
           const Seg sgm = P.seg[sg];
           const uint32_t idesc = make_idesc(sgm.n_rows);
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           }
           tc_commit(&S.d_ready);                  // accumulator complete
           a_phase ^= 1;
-          if (sgm.kind == K_FWD || sgm.kind == K_BWD || sgm.kind == K_OUT) cur ^= 1;
+          if (sgm.kind == K_FWD || sgm.kind == K_BWD || sgm.kind == K_OUT || sgm.kind == K_FOUT) cur ^= 1;
         }
       }
     }
@@ -406,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
       int64_t last_row = base + TILE_M - 1;
       if (last_row >= P.n_rows) last_row = P.n_rows - 1;
       const int64_t p_last = p_first + (rem0 + (uint32_t)(last_row - base)) / Gu;
-      uint32_t cur = 0;                            // region holding the A operand of the current segment
+      uint32_t cur = P.alt ? (uint32_t)(t & 1) : 0u;   // region holding the A operand of the current segment (see the issuer)
 
       // hand k-block kb of the A operand over to the MMA issuer
       auto signal_kb = [&](int kb) {
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         }
       };
 
-      build_a1(0, 0);
+      build_a1(0, cur);
 
       for (int sg = 0; sg < P.n_seg; ++sg) {
         const Seg sgm = P.seg[sg];
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             if (lane == 0 && (warp == 0 || warp == 15)) TR(2048 + (warp == 15 ? 2048 : 0) + sg * 16 + 1 + kb);
           }
           cur ^= 1;
-        } else if (sgm.kind == K_OUT) {
+        } else if (!X3 && sgm.kind == K_OUT) {          // (compile-time: only the bf16 instantiation has this form)
           uint32_t rr[8];
           tmem_ld8(d_addr, rr);
           const float l0 = __uint_as_float(rr[0]) + S.b_out[0], l1 = __uint_as_float(rr[1]) + S.b_out[1],
@@ -557,6 +565,91 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             const float dl0 = coef * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = coef * P.obj.c[1], dl2 = coef * P.obj.c[2];
             const int mbase = l1_hw + 6 * 16;
             quad_sync();                            // the sibling warps have read the logits too
+#pragma unroll 1
+            for (int kb = 0; kb < 4; ++kb) {
+              const int col0 = kb * 64 + hq * 16;
+              const uint32_t bits = S.mask[mbase + kb * 4 + hq][row];
+              float v[16];
+              const float4* w0 = reinterpret_cast<const float4*>(&S.w_out[0][col0]);
+              const float4* w1 = reinterpret_cast<const float4*>(&S.w_out[1][col0]);
+              const float4* w2 = reinterpret_cast<const float4*>(&S.w_out[2][col0]);
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 a0 = w0[i4], a1 = w1[i4], a2 = w2[i4];
+                const float d[4] = {dl0 * a0.x + dl1 * a1.x + dl2 * a2.x, dl0 * a0.y + dl1 * a1.y + dl2 * a2.y,
+                                    dl0 * a0.z + dl1 * a1.z + dl2 * a2.z, dl0 * a0.w + dl1 * a1.w + dl2 * a2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[i4 * 4 + e] = (bits >> mask_pos(i4 * 4 + e)) & 1u ? d[e] : 0.f;
+              }
+              store_a(dreg, kb, v);
+              signal_kb(kb);
+            }
+            cur ^= 1;
+          }
+        } else if (X3 && sgm.kind == K_FOUT) {          // (compile-time: only the fp32-grade instantiation)
+          // Last hidden layer: a8 = relu(D + b) is consumed right here by the 3-wide output layer on CUDA cores
+          // (fp32 FMAs against W_out in shared memory; the four 16-feature-group warps of a row add their partial
+          // logits through shared memory in a fixed order), so a8 never becomes an MMA operand.
+          const int mbase = l1_hw + (sgm.layer - 1) * 16;
+          float pl0 = 0.f, pl1 = 0.f, pl2 = 0.f;
+          {
+            uint32_t rr[2][16];
+            tmem_ld16_async(d_addr + (uint32_t)(hq * 16), rr[0]);
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+              tmem_ld_wait16(rr[kb & 1]);
+              if (kb + 1 < 4) tmem_ld16_async(d_addr + (uint32_t)((kb + 1) * 64 + hq * 16), rr[(kb + 1) & 1]);
+              const int col0 = kb * 64 + hq * 16;
+              const float4* b4 = reinterpret_cast<const float4*>(&S.bias[sgm.layer - 1][col0]);
+              const float4* w0 = reinterpret_cast<const float4*>(&S.w_out[0][col0]);
+              const float4* w1 = reinterpret_cast<const float4*>(&S.w_out[1][col0]);
+              const float4* w2 = reinterpret_cast<const float4*>(&S.w_out[2][col0]);
+              uint32_t m = 0;                          // sign bits of a8 in the mask_pos layout
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 bb = b4[i4], a0 = w0[i4], a1 = w1[i4], a2 = w2[i4];
+                const float zz[4] = {__uint_as_float(rr[kb & 1][i4 * 4 + 0]) + bb.x, __uint_as_float(rr[kb & 1][i4 * 4 + 1]) + bb.y,
+                                     __uint_as_float(rr[kb & 1][i4 * 4 + 2]) + bb.z, __uint_as_float(rr[kb & 1][i4 * 4 + 3]) + bb.w};
+                const float wa[4] = {a0.x, a0.y, a0.z, a0.w}, wb[4] = {a1.x, a1.y, a1.z, a1.w}, wc[4] = {a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = fmaxf(zz[e], 0.f);
+                  m |= (a > 0.f ? 1u : 0u) << mask_pos(i4 * 4 + e);
+                  pl0 = fmaf(a, wa[e], pl0); pl1 = fmaf(a, wb[e], pl1); pl2 = fmaf(a, wc[e], pl2);
+                }
+              }
+              S.mask[mbase + kb * 4 + hq][row] = (uint16_t)m;
+            }
+          }
+          S.lg[hq][row][0] = pl0; S.lg[hq][row][1] = pl1; S.lg[hq][row][2] = pl2;
+          quad_sync();
+          const float l0 = S.b_out[0] + ((S.lg[0][row][0] + S.lg[1][row][0]) + (S.lg[2][row][0] + S.lg[3][row][0]));
+          const float l1 = S.b_out[1] + ((S.lg[0][row][1] + S.lg[1][row][1]) + (S.lg[2][row][1] + S.lg[3][row][1]));
+          const float l2 = S.b_out[2] + ((S.lg[0][row][2] + S.lg[1][row][2]) + (S.lg[2][row][2] + S.lg[3][row][2]));
+          quad_sync();                              // lg may be rewritten (next tile) only after all four warps read it
+          if (hq == 0 && live && P.logits) {
+            float* o = P.logits + r_glob * 3;
+            o[0] = l0; o[1] = l1; o[2] = l2;
+          }
+          if (!P.backward) {
+            // forward only: per-pair sums of the objective over this tile's rows -> score_part[p + tile]
+            const float val = live ? coef * (P.obj.c[0] * l0 + P.obj.c[1] * l1 + P.obj.c[2] * l2 + P.obj.sq0 * l0 * l0) : 0.f;
+            if (P.G == 1) {                         // explicit-row mode: one row per pair, nothing to reduce
+              if (hq == 0 && live) P.score_part[pr + tile] = val;
+            } else
+            for (int64_t ps = p_first; ps <= p_last; ++ps) {
+              float s = (pr == ps) ? val : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+              if (hq == 0 && lane == 0) S.red_s[q] = s;
+              asm volatile("bar.sync 1, 512;" ::: "memory");
+              if (tid == 0) P.score_part[ps + tile] = (S.red_s[0] + S.red_s[1]) + (S.red_s[2] + S.red_s[3]);
+              asm volatile("bar.sync 1, 512;" ::: "memory");
+            }
+          } else {
+            // seed of the backward pass: d8 = (dObj/dlogits . W_out) * 1[a_8 > 0], written in place over the
+            // accumulator columns this warp read (the region becomes the first backward layer's A operand)
+            const float dl0 = coef * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = coef * P.obj.c[1], dl2 = coef * P.obj.c[2];
 #pragma unroll 1
             for (int kb = 0; kb < 4; ++kb) {
               const int col0 = kb * 64 + hq * 16;
@@ -775,11 +868,18 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   P.obj = *obj;
   P.n_rows = n_rows; P.n_tiles = (int)n_tiles; P.G = G; P.H1 = H1; P.opd = opd; P.n_designs = n_designs; P.n_obj = n_obj;
   P.x3 = precision == DGDM_PREC_BF16X3; P.backward = backward;
-  // forward only stops after the output layer
-  int n_seg = pl.n_seg;
-  if (!backward) { n_seg = 0; while (pl.seg[n_seg].kind != K_OUT) ++n_seg; ++n_seg; }
+  // Segment list of this launch.  The image always holds the output-layer tile; the fp32-grade plan does not use
+  // it: the last hidden layer becomes K_FOUT and the K_OUT segment is dropped.  Forward only stops after the output.
+  int n_seg = 0;
+  for (int i = 0; i < pl.n_seg; ++i) {
+    Seg sg = pl.seg[i];
+    const bool is_out = sg.kind == K_OUT;
+    if (P.x3 && is_out) { P.seg[n_seg - 1].kind = K_FOUT; }
+    else P.seg[n_seg++] = sg;
+    if (is_out && !backward) break;
+  }
   P.n_seg = n_seg;
-  for (int i = 0; i < n_seg; ++i) P.seg[i] = pl.seg[i];
+  P.alt = (P.x3 && backward) ? 1 : 0;
 
   DGDM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
