@@ -50,6 +50,20 @@ def parse(argv=None):
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--num_workers", type=int, default=4)
     p.add_argument("--ema_power", type=float, default=0.75)
+    # the reference's remaining flags (training / logging side of dynamics/parser.py): accepted so that any command line
+    # written for generator/train.py parses here too; they have no effect on sampling
+    p.add_argument("--use_sub_batch", action="store_true")
+    p.add_argument("--num_epochs", type=int, default=1000)
+    p.add_argument("--learning_rate", type=float, default=1e-4)
+    p.add_argument("--lr_warmup_steps", type=int, default=100)
+    p.add_argument("--weight_decay", type=float, default=0)
+    p.add_argument("--patience", type=int, default=500)
+    p.add_argument("--wandb_id", type=str, default=None)
+    p.add_argument("--data_dir", type=str, default="")
+    p.add_argument("--test_data_dir", type=str, default="")
+    p.add_argument("--save_ckpt_step", type=int, default=10)
+    p.add_argument("--val_step", type=int, default=100)
+    p.add_argument("--num_timesteps_per_batch", type=int, default=1)
     # additions
     p.add_argument("--objectives", type=str, default="rotate_clockwise", help="comma-separated opt_obj names")
     p.add_argument("--num_objects", type=int, default=8, help="synthetic objects when --object_dir is not given")

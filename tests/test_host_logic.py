@@ -192,3 +192,44 @@ def test_convergence_host_helpers_match_oracle():
         if lo >= 0 and up > n and lo > n:
             continue
         assert _slicer_idx(n, lo, up).tolist() == orc.slicer(torch.arange(n), lo, up).tolist()
+
+
+# ---------------------------------------------------------------------------------------------- CLI
+# every flag of the reference's parser (dynamics/parser.py:5-39) with its default
+_REF_FLAGS = {
+    "batch_size": 1024, "use_sub_batch": False, "sub_bs": 1024, "num_epochs": 1000, "num_fingers": 1000, "ctrlpts_dim": 14,
+    "ctrlpts_x_dim": 7, "ctrlpts_z_dim": 3, "learning_rate": 1e-4, "lr_warmup_steps": 100, "weight_decay": 0,
+    "patience": 500, "checkpoint_path": None, "wandb_id": None, "data_dir": "", "test_data_dir": "", "object_dir": "",
+    "num_workers": 4, "grid_size": 360, "num_pos": 9, "save_ckpt_step": 10, "val_step": 100,
+    "num_train_timesteps": 1000, "num_timesteps_per_batch": 1, "num_inference_steps": 100, "ema_power": 0.75,
+    "object_max_num_vertices": 10, "diffusion_checkpoint_path": None, "classifier_guidance": False, "num_cpus": 4,
+    "fingers_3d": False, "render_video": False, "seed": 0,
+}
+
+
+def test_cli_accepts_the_reference_command_lines():
+    """The sampler CLI parses every flag of dynamics/parser.py with the reference's defaults, and the two stock
+    command lines (generator/guided_sample_2d.sh, guided_sample_3d.sh) verbatim."""
+    from dgdm_b200 import cli
+    a = cli.parse([])
+    for k, v in _REF_FLAGS.items():
+        assert getattr(a, k) == v, k
+    cmd2d = ("--mode=test --checkpoint_path=ckpts/dynamics_2d.pt --classifier_guidance "
+             "--diffusion_checkpoint_path=ckpts/diffusion_2d.pt --object_dir=icons/Icons-50.npy --save_dir= "
+             "--ctrlpts_dim=14 --num_fingers=16 --grid_size=360 --num_pos=5 --object_max_num_vertices=100 --num_workers=0 "
+             "--num_train_timesteps=15 --num_inference_steps=5 --ema_power=0.85 --batch_size=16 --num_cpus=32 --seed=0").split()
+    a = cli.parse(cmd2d)
+    assert (a.mode, a.classifier_guidance, a.fingers_3d, a.ctrlpts_dim, a.grid_size, a.num_pos) == ("test", True, False, 14, 360, 5)
+    assert (a.num_train_timesteps, a.num_inference_steps, a.batch_size, a.object_max_num_vertices) == (15, 5, 16, 100)
+    cmd3d = ("--mode=test --checkpoint_path=ckpts/dynamics_3d.pt --diffusion_checkpoint_path=ckpts/diffusion_3d.ckpt "
+             "--object_dir= --save_dir= --classifier_guidance --num_fingers=16 --grid_size=45 --num_pos=5 --fingers_3d "
+             "--object_max_num_vertices=512 --ctrlpts_dim=42 --ctrlpts_x_dim=7 --ctrlpts_z_dim=3 --num_workers=0 "
+             "--num_train_timesteps=15 --num_inference_steps=5 --ema_power=0.85 --batch_size=16 --sub_bs=512 --num_cpus=32 "
+             "--seed=0").split()
+    a = cli.parse(cmd3d)
+    assert (a.fingers_3d, a.ctrlpts_dim, a.ctrlpts_x_dim, a.ctrlpts_z_dim, a.grid_size, a.sub_bs) == (True, 42, 7, 3, 45, 512)
+    # training is not on this path
+    with pytest.raises(SystemExit):
+        cli.main(["--mode=train", "--classifier_guidance"])
+    with pytest.raises(SystemExit):
+        cli.main(["--mode=test"])
