@@ -20,6 +20,11 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
              int opd, const int32_t* pair_object, int G, const dgdm_objective* obj, bool backward, float* dUp,
              float* score_sum, float* logits, void* ws, size_t ws_bytes, int precision, cudaStream_t s);
 size_t tc_trunk_workspace_bytes(int H1, int64_t n_pairs, int G);
+// gemm_tc.cu
+size_t gemm_tc_image_bytes(int N, int K);
+bool gemm_tc_eligible(const GemmArgs& g);
+int gemm_tc_pack(const float* W, int N, int K, void* image, cudaStream_t s);
+int gemm_tc(const GemmArgs& g, const void* wimg, int x3, int* err, cudaStream_t s);
 
 namespace {
 
@@ -209,6 +214,31 @@ __global__ void scale_kernel(float* __restrict__ out, const float* __restrict__ 
 
 inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// A linear layer at row scale (explicit-row mode, where nothing can be hoisted).  In the tensor-core modes it runs on
+// tcgen05 in fp32-grade arithmetic (bf16 hi/lo operand split, 3 MMAs per product) whenever the shape allows: the
+// weight is packed into `scratch` on the fly (a 256x256 image is 256 KB; one stream => the buffer can be reused by
+// the next layer).  N = 512 runs as two 256-column halves.  Everything else stays on the CUDA-core GEMM.
+struct RowLinear {
+  bool tc; uint8_t* scratch; int* err; cudaStream_t s;
+  int operator()(GemmArgs g) const {
+    if (tc && g.N % 256 == 0 && g.N > 256) {
+      for (int n0 = 0; n0 < g.N; n0 += 256) {
+        GemmArgs h = g;
+        h.W = g.W + (int64_t)n0 * g.K; h.bias = g.bias ? g.bias + n0 : nullptr; h.C = g.C + n0; h.N = 256;
+        if (g.mask) h.mask = g.mask + n0;
+        DGDM_TRY((*this)(h));
+      }
+      return DGDM_OK;
+    }
+    if (tc && gemm_tc_eligible(g) && gemm_tc_image_bytes(g.N, g.K) <= ROW_SCRATCH_BYTES) {
+      DGDM_TRY(gemm_tc_pack(g.W, g.N, g.K, scratch, s));
+      return gemm_tc(g, scratch, 1, err, s);
+    }
+    return gemm_f32(g, s);
+  }
+  static constexpr size_t ROW_SCRATCH_BYTES = 512 * 1024;     // K = 512, N = 256
+};
+
 struct Hoist {
   float *h0, *e, *U, *Cst, *V, *Vt, *pose, *temb, *th, *te, *tc, *oh, *oc, *dUp, *dU, *de, *dh0, *score_sum;
   int G;
@@ -396,7 +426,7 @@ extern "C" size_t dgdm_dyn_rows_workspace_bytes(const dgdm_dyn_weights* w, int64
   const int H1 = w->H1;
   size_t b = a(n_rows * 256) * 8 + a((size_t)n_rows * H1) * 7 + a(n_rows * 27) + a(2 * (size_t)H1) + a(n_rows);
   if (precision == DGDM_PREC_FP32_SIMT) b += simt_bytes(H1, n_rows);
-  else b += align_up(tc_trunk_workspace_bytes(H1, n_rows, 1), 256);
+  else b += align_up(tc_trunk_workspace_bytes(H1, n_rows, 1), 256) + RowLinear::ROW_SCRATCH_BYTES + 256;
   return b + 4096;
 }
 
@@ -435,16 +465,21 @@ extern "C" int dgdm_dyn_forward_rows(const dgdm_dyn_weights* w, const float* x, 
   h.pose = ar.take<float>(n * 27);
   float* zeros = ar.take<float>(2 * (size_t)H1);
   h.score_sum = ar.take<float>(n);
+  const bool tc = precision != DGDM_PREC_FP32_SIMT;
+  uint8_t* scratch = tc ? ar.take<uint8_t>(RowLinear::ROW_SCRATCH_BYTES) : nullptr;
+  int* lin_err = tc ? ar.take<int>(1) : nullptr;
   if (!ar.ok) { set_error("dgdm_dyn_forward_rows: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
   h.Cst = zeros; h.V = zeros + H1; h.Vt = zeros + H1;
   DGDM_CUDA(cudaMemsetAsync(zeros, 0, 2 * (size_t)H1 * sizeof(float), s));
+  if (tc) DGDM_CUDA(cudaMemsetAsync(lin_err, 0, sizeof(int), s));
+  const RowLinear lin{tc, scratch, lin_err, s};
   // every encoder at row scale -- this is the un-hoistable "paired" mode of the forward signature
-  DGDM_TRY(gemm_f32(gemm_plain(x, P, w->ge_w0, w->ge_b0, h.h0, 256, n, 256, P, ACT_RELU), s));
-  DGDM_TRY(gemm_f32(gemm_plain(h.h0, 256, w->ge_w1, w->ge_b1, h.e, 256, n, 256, 256, ACT_NONE), s));
-  DGDM_TRY(gemm_f32(gemm_plain(h.e, 256, w->w1_ctrl, nullptr, Ur, H1, n, H1, 256, ACT_NONE), s));
+  DGDM_TRY(lin(gemm_plain(x, P, w->ge_w0, w->ge_b0, h.h0, 256, n, 256, P, ACT_RELU)));
+  DGDM_TRY(lin(gemm_plain(h.h0, 256, w->ge_w1, w->ge_b1, h.e, 256, n, 256, 256, ACT_NONE)));
+  DGDM_TRY(lin(gemm_plain(h.e, 256, w->w1_ctrl, nullptr, Ur, H1, n, H1, 256, ACT_NONE)));
   pose_embed_rows_kernel<<<blocks_for(n, 128), 128, 0, s>>>(h.pose, ori, pos, n);
   DGDM_LAUNCH_CHECK();
-  DGDM_TRY(gemm_f32(gemm_plain(h.pose, 27, w->w1_pose, nullptr, Vr, H1, n, H1, 27, ACT_NONE), s));
+  DGDM_TRY(lin(gemm_plain(h.pose, 27, w->w1_pose, nullptr, Vr, H1, n, H1, 27, ACT_NONE)));
   const float* tep;
   if (w->is_3d) {
     time_embed_rows_kernel<<<blocks_for(n * 128, 256), 256, 0, s>>>(temb, t_frac, n, 256);
@@ -453,18 +488,18 @@ extern "C" int dgdm_dyn_forward_rows(const dgdm_dyn_weights* w, const float* x, 
   } else {
     time_embed_rows_kernel<<<blocks_for(n * 64, 256), 256, 0, s>>>(temb, t_frac, n, 128);
     DGDM_LAUNCH_CHECK();
-    DGDM_TRY(gemm_f32(gemm_plain(temb, 128, w->te_w0, w->te_b0, th, 256, n, 256, 128, ACT_SILU), s));
-    DGDM_TRY(gemm_f32(gemm_plain(th, 256, w->te_w1, w->te_b1, te, 256, n, 256, 256, ACT_NONE), s));
+    DGDM_TRY(lin(gemm_plain(temb, 128, w->te_w0, w->te_b0, th, 256, n, 256, 128, ACT_SILU)));
+    DGDM_TRY(lin(gemm_plain(th, 256, w->te_w1, w->te_b1, te, 256, n, 256, 256, ACT_NONE)));
     tep = te;
   }
-  DGDM_TRY(gemm_f32(gemm_plain(tep, 256, w->w1_time, w->b1, Tr, H1, n, H1, 256, ACT_NONE), s));
+  DGDM_TRY(lin(gemm_plain(tep, 256, w->w1_time, w->b1, Tr, H1, n, H1, 256, ACT_NONE)));
   const float* oc = objects;
   if (!w->is_3d) {
-    DGDM_TRY(gemm_f32(gemm_plain(objects, w->obj_dim, w->oe_w0, w->oe_b0, h.oh, 256, n, 256, w->obj_dim, ACT_RELU), s));
-    DGDM_TRY(gemm_f32(gemm_plain(h.oh, 256, w->oe_w1, w->oe_b1, h.oc, 256, n, 256, 256, ACT_NONE), s));
+    DGDM_TRY(lin(gemm_plain(objects, w->obj_dim, w->oe_w0, w->oe_b0, h.oh, 256, n, 256, w->obj_dim, ACT_RELU)));
+    DGDM_TRY(lin(gemm_plain(h.oh, 256, w->oe_w1, w->oe_b1, h.oc, 256, n, 256, 256, ACT_NONE)));
     oc = h.oc;
   }
-  DGDM_TRY(gemm_f32(gemm_plain(oc, 256, w->w1_obj, nullptr, Or, H1, n, H1, 256, ACT_NONE), s));
+  DGDM_TRY(lin(gemm_plain(oc, 256, w->w1_obj, nullptr, Or, H1, n, H1, 256, ACT_NONE)));
   sum4_kernel<<<blocks_for(n * H1 / 4, 256), 256, 0, s>>>(h.U, Or, Ur, Vr, Tr, n * H1 / 4);
   DGDM_LAUNCH_CHECK();
   dgdm_objective dummy{{0.f, 0.f, 0.f}, 0.f, nullptr};
@@ -474,11 +509,11 @@ extern "C" int dgdm_dyn_forward_rows(const dgdm_dyn_weights* w, const float* x, 
     return DGDM_OK;
   }
   DGDM_TRY(trunk_dispatch(w, h, (int)n, 1, 1, nullptr, ob, true, logits, ar, precision, s));
-  DGDM_TRY(gemm_f32(gemm_plain(h.dUp, H1, w->w1_ctrl_t, nullptr, h.de, 256, n, 256, H1, ACT_NONE), s));
+  DGDM_TRY(lin(gemm_plain(h.dUp, H1, w->w1_ctrl_t, nullptr, h.de, 256, n, 256, H1, ACT_NONE)));
   GemmArgs g = gemm_plain(h.de, 256, w->ge_w1_t, nullptr, h.dh0, 256, n, 256, 256, ACT_NONE);
   g.mask = h.h0;
-  DGDM_TRY(gemm_f32(g, s));
-  DGDM_TRY(gemm_f32(gemm_plain(h.dh0, 256, w->ge_w0_t, nullptr, grad_x, P, n, P, 256, ACT_NONE), s));
+  DGDM_TRY(lin(g));
+  DGDM_TRY(lin(gemm_plain(h.dh0, 256, w->ge_w0_t, nullptr, grad_x, P, n, P, 256, ACT_NONE)));
   return DGDM_OK;
 }
 

@@ -15,7 +15,8 @@
 //   warp 13    MMA issuer: tcgen05.mma.cta_group::1.kind::f16, A and B from shared memory, M=128 x N x K=16,
 //              fp32 accumulators in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i overlaps
 //              the main loop of tile i+1.
-//   warps 0-3  epilogue: tcgen05.ld, + bias, activation, 128-bit stores through the C row mapping.
+//   warps 0-3  epilogue: tcgen05.ld, + bias, activation, optional mask (zero where mask <= 0), 128-bit stores through
+//              the C row mapping.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
       const int64_t m = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TM + r;
       const bool live = m < g.M;
       float* crow = g.C + (live ? (m / g.c_lr) * g.c_ss + (m % g.c_lr) * g.c_rs : 0);
+      const float* mrow = (g.mask && live) ? g.mask + (m / g.m_lr) * g.m_ss + (m % g.m_lr) * g.m_rs : nullptr;
       bar_wait(&S.d_full[acc], (t >> 1) & 1, P.err, 16);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemm_tc_kernel(const __grid_constant_
               if (g.bias) v += __ldg(g.bias + c * 32 + i + e);
               if (g.act == ACT_RELU) v = fmaxf(v, 0.f);
               else if (g.act == ACT_SILU) v = v / (1.f + expf(-v));
+              if (mrow && !(__ldg(mrow + c * 32 + i + e) > 0.f)) v = 0.f;      // ReLU backward: zero where mask <= 0
               po[e] = v;
             }
             *reinterpret_cast<float4*>(crow + c * 32 + i) = o;
@@ -293,7 +296,7 @@ size_t gemm_tc_image_bytes(int N, int K) { return (size_t)(K / KB) * 2 * N * 128
 bool gemm_tc_eligible(const GemmArgs& g) {
   return (g.N == 128 || g.N == 256) && g.K % KB == 0 && g.a_ct % KB == 0 && g.a_ss % 4 == 0 && g.a_rs % 4 == 0 &&
          g.a_ts % 4 == 0 && g.c_ss % 4 == 0 && g.c_rs % 4 == 0 && ((uintptr_t)g.A) % 16 == 0 && ((uintptr_t)g.C) % 16 == 0 &&
-         g.mask == nullptr && g.add == nullptr && g.M > 0;
+         g.add == nullptr && g.M > 0;
 }
 
 int gemm_tc_pack(const float* W, int N, int K, void* image, cudaStream_t s) {

@@ -156,7 +156,8 @@ int dgdm_dyn_score(const dgdm_dyn_weights* w, const float* x, int32_t n_designs,
  * 500,516), where every row brings its own finger, pose, time and object, so nothing can be hoisted (BASELINE.json
  * configs[3], the "paired" throughput sweep).  x [N,P]; ori [N]; pos [N,2]; t_frac [N]; objects 2D [N,obj_dim] /
  * 3D [N,256] PointNet++ codes.  logits [N,3] (out, may be NULL).  If grad_x != NULL it receives
- * d/dx_r objective(logits_r), [N,P] (forward + input-gradient). */
+ * d/dx_r objective(logits_r), [N,P] (forward + input-gradient).  In the tensor-core modes the row-scale encoder
+ * layers with K % 64 == 0 also run on tcgen05 (fp32-grade operand split, weights packed into the workspace per call). */
 size_t dgdm_dyn_rows_workspace_bytes(const dgdm_dyn_weights* w, int64_t n_rows, int32_t precision);
 int dgdm_dyn_forward_rows(const dgdm_dyn_weights* w, const float* x, const float* ori, const float* pos,
                           const float* t_frac, const float* objects, int64_t n_rows, const dgdm_objective* objective,
@@ -238,7 +239,7 @@ int dgdm_best_of_n(const float* scores, int32_t n_obj, int32_t n_cand, int32_t k
  */
 int dgdm_linear_f32(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
                     int64_t M, int32_t N, int32_t K, int32_t relu, void* stream);
-/* Same contraction on the tcgen05 path (K %% 64 == 0, N in {128,256}); packs W into the workspace first. */
+/* Same contraction on the tcgen05 path (K % 64 == 0, N in {128,256}); packs W into the workspace first. */
 size_t dgdm_linear_tc_workspace_bytes(int32_t N, int32_t K);
 int dgdm_linear_tc(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int64_t M,
                    int32_t N, int32_t K, int32_t relu, int32_t precision, void* workspace, size_t workspace_bytes,
