@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16x3", "bf16", "fp16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=["c2", "c2g36", "c3", "c5"])
     args = ap.parse_args()
@@ -283,7 +283,7 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        x3 = args.precision == "fp32"
+        x3 = args.precision in ("fp32", "fp16x3")
         # dominant kernel: all launches inside the timed region (5 backward + 1 forward-only per pass)
         G = GRID * NPOS * NPOS
         bwd_rows = (hi - lo) * N_CAND * G * T_INF * args.steps

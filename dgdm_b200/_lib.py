@@ -11,8 +11,8 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdgdm_b200.so")
 
-PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "fp32": PREC_BF16X3, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_FP16, PREC_FP16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "fp32": PREC_BF16X3, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
 
 fp = C.c_void_p  # device pointers travel as integers
 
@@ -57,6 +57,7 @@ EXPORTS = {
     "dgdm_launch_count": (C.c_uint64, []),
     "dgdm_trunk_timing": (C.c_int, [C.c_int32]),
     "dgdm_trunk_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "dgdm_trunk_timing_read_split": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dgdm_ddim_guided_update": (C.c_int, [fp, fp, fp, fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                           C.c_float, C.c_int, fp]),
     "dgdm_dyn_tc_image_bytes": (C.c_size_t, [C.c_int32]),
@@ -125,6 +126,8 @@ def ptr(t) -> Optional[int]:
     return t.data_ptr()
 
 
-def stream_ptr() -> int:
+def stream_ptr(device=None) -> int:
+    """Current stream of ``device`` (default: the current device).  Callers launch inside
+    ``torch.cuda.device(device)`` so that the library's cudaGetDevice()/launch context matches the pointers."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

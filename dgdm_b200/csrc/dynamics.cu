@@ -406,7 +406,9 @@ int trunk_dispatch(const dgdm_dyn_weights* w, const Hoist& h, int nd, int n_obj,
                    const dgdm_objective* obj, bool backward, float* logits, Arena& ar, int precision, cudaStream_t s) {
   if (precision == DGDM_PREC_FP32_SIMT)
     return simt_trunk(w, h, nd, n_obj, opd, pair_object, obj, backward, logits, ar, s);
-  DGDM_CHECK_ARG(precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_BF16, "dynamics: unknown precision %d", precision);
+  DGDM_CHECK_ARG(precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_BF16 || precision == DGDM_PREC_FP16 ||
+                     precision == DGDM_PREC_FP16X3,
+                 "dynamics: unknown precision %d", precision);
   DGDM_CHECK_ARG(w->tc_image != nullptr, "dynamics: tensor-core precision requested but weights carry no tc_image "
                                          "(call dgdm_dyn_pack_tc)");
   size_t need = tc_trunk_workspace_bytes(w->H1, h.n_pairs, h.G);

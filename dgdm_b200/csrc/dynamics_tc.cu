@@ -24,10 +24,21 @@
 // TMEM: two 256-column regions that swap roles every layer (A operand, per 16-feature group [hi 8 | lo 8] columns,
 // and fp32 accumulator); the epilogue rewrites the accumulator in place into the next A operand.
 //
-// Precision modes: BF16X3 splits both operands into bf16 hi + lo and issues 3 MMAs (hi*hi, lo*hi, hi*lo) into
-// the same fp32 accumulator: ~2^-16 relative product error, fp32-grade (<=1e-3 end to end).  BF16 issues one.
+// Why the accumulator is NOT split into N = 128 halves (round-2 experiment, scripts/dev/experiments/): issuing a
+// layer as interleaved (half, k-block) units hides the accumulate -> epilogue -> next-layer chain (issuer waits drop
+// from ~1000 to ~70 cycles per layer), but a TS-mode N = 128 MMA has to fetch its 4 KB A operand from TMEM every 64
+// cycles, and that fetch loses against the epilogue warps' tcgen05.ld/st traffic: 64.0 cycles per MMA alone, 88-101
+// with 16 epilogue warps active (scripts/microbench/mma_tmem_conflict.cu); an N = 256 MMA stays at 128.0.  Net: no
+// gain (fp32-grade 0.917 vs 0.91, bf16 0.67 vs 0.70 of roofline), so a layer is issued as N = 256 MMAs.
+//
+// Precision modes: BF16X3 / FP16X3 split both operands into 16-bit hi + lo parts and issue 3 MMAs (hi*hi, lo*hi,
+// hi*lo) into the same fp32 accumulator (bf16 parts: ~2^-16 relative product error; fp16 parts with the operand
+// scaling below: ~2^-21), fp32-grade (<=1e-3 end to end).  BF16 and FP16 issue one MMA per product with bf16 / fp16
+// operands (fp16: 3 more mantissa bits, ~8x fewer ReLU sign flips).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -37,7 +48,15 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int KBLK = 64;                       // bf16 elements per k-block row = 128 bytes = one swizzle span
-constexpr int WTILE_BYTES = 256 * KBLK * 2;    // 32 KB: 256 rows x 128 B
+constexpr int WTILE_BYTES = 256 * KBLK * 2;    // 32 KB ring slot: 256 rows x 128 B
+// Operand scaling of the fp16 modes (all powers of two, so exact).  An fp16 residual part is ~2^-11 of its value and
+// falls below the smallest normal fp16 (6.1e-5) for |value| < 0.125 -- every weight of this network, most activations
+// and gradients -- where it keeps fewer and fewer bits (measured: unscaled fp16 hi+lo operands were 2x LESS accurate
+// than bf16 hi+lo).  So the weight image holds W * SW, activations live in TMEM as a * SA and backward operands as
+// d * GS; the epilogues undo SW with the multiply they already do (forward: fma(D, 1/SW, SA*b)) or one FMUL (backward).
+constexpr float F16_SW = 256.f;                // weights
+constexpr float F16_SA = 64.f;                 // forward activations
+constexpr float F16_GS = 64.f;                 // backward operands (seed); undone by reduce_slots together with SW
 constexpr int NSTAGE = 5;
 constexpr int NEPI = 16;                       // epilogue warps: 4 per TMEM lane quadrant, 16 features of every k-block each
 constexpr int NTHREADS = (NEPI + 2) * 32;      // + producer warp + MMA warp
@@ -68,6 +87,7 @@ struct TcParams {
   dgdm_objective obj;
   int64_t n_rows;       // n_pairs * G
   int n_tiles, G, H1, opd, n_designs, n_obj, n_seg, x3, backward;
+  float gscale;         // scale of the backward seed (1, or F16_GS in the fp16 modes)
   int alt;              // 1: an odd number of region swaps per tile -> alternate the start region tile by tile
   Seg seg[MAX_SEG];
 };
@@ -109,11 +129,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// tc_commit / tc_mma_ts are called by every lane of the issuing warp; lane 0 executes the instruction
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  if ((threadIdx.x & 31) == 0)
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // D[tmem] (+)= A[tmem] . B[smem]^T ; kind::f16 (bf16 in, fp32 accumulate)
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  if ((threadIdx.x & 31) == 0)
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -161,9 +184,10 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// Instruction descriptor: D fp32, A/B bf16 (format 1) or fp16 (format 0), both K-major, M = 128, N = n.
+template <bool F16>
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (F16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
 __device__ __forceinline__ int pair_obj(int64_t p, int opd, int n_designs, int n_obj, const int32_t* pair_object) {
@@ -177,11 +201,45 @@ __device__ __forceinline__ int pair_obj(int64_t p, int opd, int n_designs, int n
   return p <= 0x7fffffffll ? (int)((uint32_t)p % (uint32_t)opd) : (int)(p % opd);
 }
 
-// Split 32 fp32 values into packed bf16 hi (and lo = rn(v - hi)) pairs; element 2i in the low half.
-template <bool X3>
+// accumulator word -> value with the weight scale of the fp16 modes removed (see F16_SW)
+template <bool F16>
+__device__ __forceinline__ float unscale(uint32_t acc) {
+  return F16 ? __uint_as_float(acc) * (1.f / F16_SW) : __uint_as_float(acc);
+}
+template <bool F16>
+__device__ __forceinline__ float unscale_add(uint32_t acc, float b) {
+  return F16 ? fmaf(__uint_as_float(acc), 1.f / F16_SW, b) : __uint_as_float(acc) + b;
+}
+
+__device__ __forceinline__ uint32_t cvt_rn_f16x2(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_rn_relu_f16x2(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_rz_relu_f16x2(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+
+// Split 16 fp32 values into packed 16-bit hi (and, X3, bf16 lo = rn(v - hi)) pairs; element 2i in the low half.
+template <bool X3, bool F16>
 __device__ __forceinline__ void split_pack(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
+    if (F16) {
+      hi[i] = cvt_rn_f16x2(v[2 * i], v[2 * i + 1]);
+      if (X3) {
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi[i]));
+        lo[i] = cvt_rn_f16x2(v[2 * i] - h.x, v[2 * i + 1] - h.y);
+      }
+      continue;
+    }
     __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     hi[i] = *reinterpret_cast<uint32_t*>(&h);
     if (X3) {
@@ -211,13 +269,19 @@ __device__ __forceinline__ uint32_t cvt_rn_relu_bf16x2(float lo_elem, float hi_e
 // bit position of element e (0..15) inside the 16-bit sign word produced by relu_split16
 __host__ __device__ constexpr int mask_pos(int e) { return ((e & 1) * 8) + (((e >> 1) & 1) * 4) + 3 - (e >> 2); }
 
-// z[16] (pre-activation) -> packed bf16 hi[8] (+ lo[8]) of relu(z), returns the 16 sign bits (mask_pos layout).
-// A value whose bf16 exponent field is < 2 (|z| < 2^-125) counts as zero.
-template <bool X3>
-__device__ __forceinline__ uint32_t relu_split16(const float (&z)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+// z[16] (pre-activation) -> packed 16-bit hi[8] (+ bf16 lo[8]) of relu(z).
+template <bool X3, bool F16>
+__device__ __forceinline__ void relu_split16(const float (&z)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (X3) {
+    if (F16 && X3) {
+      // hi truncated (z - hi >= 0 for z >= 0), so the residual goes through the same .relu conversion
+      hi[i] = cvt_rz_relu_f16x2(z[2 * i], z[2 * i + 1]);
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi[i]));
+      lo[i] = cvt_rn_relu_f16x2(z[2 * i] - h.x, z[2 * i + 1] - h.y);
+    } else if (F16) {
+      hi[i] = cvt_rn_relu_f16x2(z[2 * i], z[2 * i + 1]);
+    } else if (X3) {
       hi[i] = cvt_rz_relu_bf16x2(z[2 * i], z[2 * i + 1]);
       const float h0 = __uint_as_float(hi[i] << 16), h1 = __uint_as_float(hi[i] & 0xFFFF0000u);
       lo[i] = cvt_rn_relu_bf16x2(z[2 * i] - h0, z[2 * i + 1] - h1);
@@ -225,10 +289,16 @@ __device__ __forceinline__ uint32_t relu_split16(const float (&z)[16], uint32_t 
       hi[i] = cvt_rn_relu_bf16x2(z[2 * i], z[2 * i + 1]);
     }
   }
+}
+// The 16 sign bits (mask_pos layout) of the packed hi words of relu(z).  Computed AFTER the k-block has been handed to
+// the MMA issuer: the ~20 ALU instructions are then off the accumulate -> epilogue -> next-layer critical path.
+// A value whose top byte is zero counts as zero: bf16 exponent field < 2 (|z| < 2^-125); fp16 z < 2^-16 (a
+// subnormal below a quarter of the smallest normal -- 30x below the fp16 rounding noise of an O(1) pre-activation).
+__device__ __forceinline__ uint32_t sign_bits16(const uint32_t (&hi)[8]) {
   uint32_t m = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    // exponent bytes of elements 4k..4k+3 -> one word; byte != 0  <=>  (byte + 0x7F) has its MSB set
+    // top bytes of elements 4k..4k+3 -> one word; byte != 0  <=>  (byte + 0x7F) has its MSB set
     const uint32_t t = __byte_perm(hi[2 * k], hi[2 * k + 1], 0x7531) + 0x7F7F7F7Fu;
     m |= (t & 0x80808080u) >> k;
   }
@@ -258,8 +328,11 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 #ifdef DGDM_TRUNK_TRACE
 __device__ long long g_trace[8192];
 #define TR(slot) do { if (blockIdx.x == 0 && t == 2) g_trace[slot] = clock64(); } while (0)
+// epilogue warp 0, k-block 0 of segment tr_sg: fine-grained stamps of the hand-off chain (slots 2048 + sg*16 + 6..10)
+#define TRE(kb, k) do { if ((kb) == 0 && warp == 0 && lane == 0) TR(2048 + tr_sg * 16 + (k)); } while (0)
 #else
 #define TR(slot) do { } while (0)
+#define TRE(kb, k) do { } while (0)
 #endif
 
 struct Smem {
@@ -274,14 +347,19 @@ struct Smem {
   uint16_t mask[2 * MASK_WORDS][TILE_M];      // ReLU sign bits, one halfword per (16-feature group, row)
 };
 
-template <bool X3>
+template <bool X3, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // weight ring first (1024-byte aligned for the 128B swizzle), bookkeeping after
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer + offset, not an integer round trip: the compiler then keeps the shared address space and emits LDS/STS
+  // for the bias / sign-bit accesses instead of generic loads and stores)
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Smem& S = *reinterpret_cast<Smem*>(ring + NSTAGE * WTILE_BYTES);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index through a shuffle: the compiler then knows it is warp-uniform, and the MMA issuer below -- executed by
+  // all 32 lanes of its warp, only the instructions themselves predicated on lane 0 -- keeps every tcgen05.mma operand
+  // in uniform registers (inside an `if (lane == 0)` region each MMA paid an R2UR of its operand address)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
@@ -289,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
     mbar_init(&S.d_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 7 * 256; i += NTHREADS) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256];
+  for (int i = tid; i < 7 * 256; i += NTHREADS) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256] * (F16 ? F16_SA : 1.f);
   for (int i = tid; i < 3 * 256; i += NTHREADS) S.w_out[i / 256][i % 256] = P.w_out[i];
   if (tid < 3) S.b_out[tid] = P.b_out[tid];
   if (warp == NEPI + 1) {
@@ -334,10 +412,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
     // =============================== MMA issuer ===============================
     // TMEM is two 256-column regions.  During a segment the A operand lives in region `cur` (per 64-wide
     // K=16 step ks of k-block kb: hi at [64kb+16ks, +8), lo at [64kb+16ks+8, +8)) and the accumulator in the other one.
-    // The epilogue converts the accumulator IN PLACE into the next layer's A operand, k-block by k-block,
-    // and hands each k-block over on its own mbarrier, so the next layer's MMAs start after a quarter of the
-    // epilogue instead of all of it; the roles of the two regions then swap.
-    if (lane == 0) {
+    // The epilogue converts the accumulator IN PLACE into the next layer's A operand, k-block by k-block, and hands
+    // each k-block over on its own mbarrier, so the next layer's MMAs start after a quarter of the epilogue instead
+    // of all of it; the roles of the two regions then swap.
+    {   // whole warp, uniform control flow; tc_mma_ts / tc_commit issue from lane 0
       uint32_t stage = 0, phase = 0, a_phase = 0;
       for (int t = 0; t < tiles_mine; ++t) {
         // fused-output plan: 13 region swaps per backward tile: alternate the start region so that the next tile's layer-1 operand lands in
@@ -345,8 +423,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         uint32_t cur = P.alt ? (uint32_t)(t & 1) : 0u;
         for (int sg = 0; sg < P.n_seg; ++sg) {
           const Seg sgm = P.seg[sg];
-          const uint32_t idesc = make_idesc(sgm.n_rows);
           const uint32_t a_base = cur * 256u, d_base = (cur ^ 1u) * 256u;      // TMEM base is 0 (checked above)
+          const uint32_t idesc = make_idesc<F16>(sgm.n_rows);
           uint32_t accum = sgm.accum;
           for (int j = 0; j < tiles_per_seg; ++j) {
             const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;
@@ -363,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 #pragma unroll
             for (int ks = 0; ks < KBLK / 16; ++ks) {
               const uint64_t bdesc = make_b_desc(b_addr + ks * 32);
-              const uint32_t a_col = (uint32_t)(kb * 64 + ks * 16);            // 16 bf16 = 8 TMEM columns: [hi 8 | lo 8]
+              const uint32_t a_col = (uint32_t)(kb * 64 + ks * 16);            // 16 operand elements = 8 TMEM columns: [hi 8 | lo 8]
               tc_mma_ts(d_base, a_base + a_col, bdesc, idesc, accum);
               accum = 1;
               if (X3 && part == 0) tc_mma_ts(d_base, a_base + a_col + 8, bdesc, idesc, 1);
@@ -417,11 +495,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
       uint32_t cur = P.alt ? (uint32_t)(t & 1) : 0u;   // region holding the A operand of the current segment (see the issuer)
 
       // hand k-block kb of the A operand over to the MMA issuer
+      [[maybe_unused]] int tr_sg = 0;
       auto signal_kb = [&](int kb) {
         tmem_wait_st();
+        TRE(kb, 9);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.a_ready[kb]);
+        TRE(kb, 10);
       };
       // store 16 features (k-block kb, group hq) of this row as bf16 hi [+ lo] into region `reg`
       auto store_packed = [&](uint32_t reg, int kb, const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
@@ -433,7 +514,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
       };
       auto store_a = [&](uint32_t reg, int kb, const float (&v)[16]) {
         uint32_t hi[8], lo[8];
-        split_pack<X3>(v, hi, lo);
+        split_pack<X3, F16>(v, hi, lo);
         store_packed(reg, kb, hi, lo);
       };
       // layer-1 activations for K-half `kh` -> A operand in region `reg` + layer-1 sign bits
@@ -456,6 +537,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + i);
             a.x = (k4.x + u4.x) + pv[i]; a.y = (k4.y + u4.y) + pv[i + 1]; a.z = (k4.z + u4.z) + pv[i + 2]; a.w = (k4.w + u4.w) + pv[i + 3];
           }
+          if (F16) { a.x *= F16_SA; a.y *= F16_SA; a.z *= F16_SA; a.w *= F16_SA; }     // fp16 modes: operands are a * SA
           z[i] = a.x; z[i + 1] = a.y; z[i + 2] = a.z; z[i + 3] = a.w;
         }
       };
@@ -470,9 +552,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             float z[16];
             load_z(kh * 256 + kb * 64 + hq * 16, z);
             uint32_t hi[8], lo[8];
-            S.mask[kh * 16 + kb * 4 + hq][row] = (uint16_t)relu_split16<X3>(z, hi, lo);
+            relu_split16<X3, F16>(z, hi, lo);
             store_packed(reg, kb, hi, lo);
             signal_kb(kb);
+            S.mask[kh * 16 + kb * 4 + hq][row] = (uint16_t)sign_bits16(hi);
           }
         } else {
         float zb[2][16];
@@ -481,9 +564,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         for (int kb = 0; kb < 4; ++kb) {
           if (kb + 1 < 4) load_z(kh * 256 + (kb + 1) * 64 + hq * 16, zb[(kb + 1) & 1]);
           uint32_t hi[8], lo[8];
-          S.mask[kh * 16 + kb * 4 + hq][row] = (uint16_t)relu_split16<X3>(zb[kb & 1], hi, lo);
+          relu_split16<X3, F16>(zb[kb & 1], hi, lo);
           store_packed(reg, kb, hi, lo);
           signal_kb(kb);
+          S.mask[kh * 16 + kb * 4 + hq][row] = (uint16_t)sign_bits16(hi);
         }
         }
       };
@@ -495,6 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         const bool last_seg = sg == P.n_seg - 1;
         const uint32_t dreg = cur ^ 1u;             // accumulator region of this segment
         const uint32_t d_addr = lane_addr + dreg * 256u;
+        tr_sg = sg;
         mbar_wait(&S.d_ready, d_phase, P.err, 4);
         d_phase ^= 1;
         tc_fence_after();
@@ -510,37 +595,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
             tmem_ld_wait16(rr[kb & 1]);
+            TRE(kb, 6);
             if (kb + 1 < 4) tmem_ld16_async(d_addr + (uint32_t)((kb + 1) * 64 + hq * 16), rr[(kb + 1) & 1]);
             if (sgm.kind == K_FWD) {
               const float4* b4 = reinterpret_cast<const float4*>(&S.bias[sgm.layer - 1][kb * 64 + hq * 16]);
               float z[16];
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 bb = b4[i4];
-                z[i4 * 4 + 0] = __uint_as_float(rr[kb & 1][i4 * 4 + 0]) + bb.x;
-                z[i4 * 4 + 1] = __uint_as_float(rr[kb & 1][i4 * 4 + 1]) + bb.y;
-                z[i4 * 4 + 2] = __uint_as_float(rr[kb & 1][i4 * 4 + 2]) + bb.z;
-                z[i4 * 4 + 3] = __uint_as_float(rr[kb & 1][i4 * 4 + 3]) + bb.w;
+                const float4 bb = b4[i4];                // (fp16 modes: SA * b; D = SA * SW * (a . w))
+                z[i4 * 4 + 0] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 0], bb.x);
+                z[i4 * 4 + 1] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 1], bb.y);
+                z[i4 * 4 + 2] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 2], bb.z);
+                z[i4 * 4 + 3] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 3], bb.w);
               }
               uint32_t hi[8], lo[8];
-              S.mask[mbase + kb * 4 + hq][row] = (uint16_t)relu_split16<X3>(z, hi, lo);
+              relu_split16<X3, F16>(z, hi, lo);
+              TRE(kb, 7);
               store_packed(dreg, kb, hi, lo);       // in place: the accumulator region becomes the next A operand
+              TRE(kb, 8);
+              signal_kb(kb);
+              S.mask[mbase + kb * 4 + hq][row] = (uint16_t)sign_bits16(hi);   // after the hand-off: off the critical path
             } else {
               const uint32_t bits = S.mask[mbase + kb * 4 + hq][row];
               float v[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = (bits >> mask_pos(i)) & 1u ? __uint_as_float(rr[kb & 1][i]) : 0.f;
+              for (int i = 0; i < 16; ++i) v[i] = (bits >> mask_pos(i)) & 1u ? unscale<F16>(rr[kb & 1][i]) : 0.f;
+              TRE(kb, 7);
               store_a(dreg, kb, v);
+              TRE(kb, 8);
+              signal_kb(kb);
             }
-            signal_kb(kb);
             if (lane == 0 && (warp == 0 || warp == 15)) TR(2048 + (warp == 15 ? 2048 : 0) + sg * 16 + 1 + kb);
           }
           cur ^= 1;
         } else if (!X3 && sgm.kind == K_OUT) {          // (compile-time: only the bf16 instantiation has this form)
           uint32_t rr[8];
           tmem_ld8(d_addr, rr);
-          const float l0 = __uint_as_float(rr[0]) + S.b_out[0], l1 = __uint_as_float(rr[1]) + S.b_out[1],
-                      l2 = __uint_as_float(rr[2]) + S.b_out[2];
+          constexpr float inv_out = F16 ? 1.f / (F16_SA * F16_SW) : 1.f;       // D = SA * SW * (a8 . w_out)
+          const float l0 = __uint_as_float(rr[0]) * inv_out + S.b_out[0], l1 = __uint_as_float(rr[1]) * inv_out + S.b_out[1],
+                      l2 = __uint_as_float(rr[2]) * inv_out + S.b_out[2];
           if (hq == 0 && live && P.logits) {
             float* o = P.logits + r_glob * 3;
             o[0] = l0; o[1] = l1; o[2] = l2;
@@ -562,7 +655,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             }
           } else {
             // seed of the backward pass: d8 = (dObj/dlogits . W_out) * 1[a_8 > 0], written over the logits' region
-            const float dl0 = coef * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = coef * P.obj.c[1], dl2 = coef * P.obj.c[2];
+            const float cg = coef * P.gscale;
+            const float dl0 = cg * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = cg * P.obj.c[1], dl2 = cg * P.obj.c[2];
             const int mbase = l1_hw + 6 * 16;
             quad_sync();                            // the sibling warps have read the logits too
 #pragma unroll 1
@@ -608,8 +702,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
                 const float4 bb = b4[i4], a0 = w0[i4], a1 = w1[i4], a2 = w2[i4];
-                const float zz[4] = {__uint_as_float(rr[kb & 1][i4 * 4 + 0]) + bb.x, __uint_as_float(rr[kb & 1][i4 * 4 + 1]) + bb.y,
-                                     __uint_as_float(rr[kb & 1][i4 * 4 + 2]) + bb.z, __uint_as_float(rr[kb & 1][i4 * 4 + 3]) + bb.w};
+                const float zz[4] = {unscale_add<F16>(rr[kb & 1][i4 * 4 + 0], bb.x), unscale_add<F16>(rr[kb & 1][i4 * 4 + 1], bb.y),
+                                     unscale_add<F16>(rr[kb & 1][i4 * 4 + 2], bb.z), unscale_add<F16>(rr[kb & 1][i4 * 4 + 3], bb.w)};
                 const float wa[4] = {a0.x, a0.y, a0.z, a0.w}, wb[4] = {a1.x, a1.y, a1.z, a1.w}, wc[4] = {a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -621,6 +715,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
               S.mask[mbase + kb * 4 + hq][row] = (uint16_t)m;
             }
           }
+          if (F16) { pl0 *= 1.f / F16_SA; pl1 *= 1.f / F16_SA; pl2 *= 1.f / F16_SA; }     // a8 above is SA * relu(z8)
           S.lg[hq][row][0] = pl0; S.lg[hq][row][1] = pl1; S.lg[hq][row][2] = pl2;
           quad_sync();
           const float l0 = S.b_out[0] + ((S.lg[0][row][0] + S.lg[1][row][0]) + (S.lg[2][row][0] + S.lg[3][row][0]));
@@ -649,7 +744,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           } else {
             // seed of the backward pass: d8 = (dObj/dlogits . W_out) * 1[a_8 > 0], written in place over the
             // accumulator columns this warp read (the region becomes the first backward layer's A operand)
-            const float dl0 = coef * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = coef * P.obj.c[1], dl2 = coef * P.obj.c[2];
+            const float cg = coef * P.gscale;
+            const float dl0 = cg * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = cg * P.obj.c[1], dl2 = cg * P.obj.c[2];
 #pragma unroll 1
             for (int kb = 0; kb < 4; ++kb) {
               const int col0 = kb * 64 + hq * 16;
@@ -735,7 +831,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 }
 
 // K2 tail: dUp[p,:] = sum over the tiles covering pair p of part[p + tile,:], ascending tile order.
-__global__ void reduce_slots_kernel(float* __restrict__ dUp, const float* __restrict__ part, int64_t n_pairs, int G, int H1) {
+__global__ void reduce_slots_kernel(float* __restrict__ dUp, const float* __restrict__ part, int64_t n_pairs, int G, int H1,
+                                    float inv_gscale) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_pairs * H1) return;
   int64_t p = idx / H1;
@@ -743,7 +840,7 @@ __global__ void reduce_slots_kernel(float* __restrict__ dUp, const float* __rest
   int64_t t0 = (p * G) / TILE_M, t1 = ((p + 1) * G - 1) / TILE_M;
   float s = 0.f;
   for (int64_t t = t0; t <= t1; ++t) s += part[(p + t) * H1 + c];
-  dUp[idx] = s;
+  dUp[idx] = s * inv_gscale;          // exact: the scale is a power of two
 }
 __global__ void reduce_score_slots_kernel(float* __restrict__ out, const float* __restrict__ part, int64_t n_pairs, int G) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -759,8 +856,9 @@ __global__ void reduce_score_slots_kernel(float* __restrict__ out, const float* 
 // ---------------------------------------------------------------------------------------------
 struct PackSeg { const float* src; int ld; int k0; int n_valid; int n_rows; uint32_t img_off; };
 
-// one thread per 16-byte chunk (8 bf16) of a tile
-__global__ void pack_tc_kernel(uint8_t* __restrict__ img, PackSeg ps) {
+// one thread per 16-byte chunk (8 elements) of a tile; image order inside a segment: kb0.hi, kb0.lo, kb1.hi, ...
+// `f16`: fp16 hi/lo instead of bf16 hi/lo.
+__global__ void pack_tc_kernel(uint8_t* __restrict__ img, PackSeg ps, int f16) {
   const int tile_bytes = ps.n_rows * 128;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int chunks_per_tile = ps.n_rows * 8;
@@ -768,12 +866,20 @@ __global__ void pack_tc_kernel(uint8_t* __restrict__ img, PackSeg ps) {
   const int tl = idx / chunks_per_tile, rem = idx % chunks_per_tile;
   const int kb = tl >> 1, part = tl & 1;
   const int n = rem / 8, j = rem % 8;
-  __nv_bfloat16 out[8];
+  uint16_t out[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     float w = n < ps.n_valid ? ps.src[(int64_t)n * ps.ld + ps.k0 + kb * KBLK + j * 8 + e] : 0.f;
-    __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    out[e] = part == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+    if (f16) {
+      w *= F16_SW;
+      __half hi = __float2half_rn(w);
+      __half v = part == 0 ? hi : __float2half_rn(w - __half2float(hi));
+      out[e] = *reinterpret_cast<uint16_t*>(&v);
+    } else {
+      __nv_bfloat16 hi = __float2bfloat16_rn(w);
+      __nv_bfloat16 v = part == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+      out[e] = *reinterpret_cast<uint16_t*>(&v);
+    }
   }
   // 128B swizzle: 16-byte chunk j of row n lands at chunk (j ^ (n & 7))
   uint8_t* dst = img + ps.img_off + (size_t)tl * tile_bytes + (size_t)n * 128 + ((j ^ (n & 7)) * 16);
@@ -814,9 +920,14 @@ Plan make_plan(const dgdm_dyn_weights* w, int H1) {
 size_t smem_bytes() { return 1024 + (size_t)NSTAGE * WTILE_BYTES + sizeof(Smem); }
 
 // event-pair timing of the trunk kernel (bench.py roofline)
+// Off by default.  Launches made while the stream is being captured into a CUDA graph are not timed (events cannot
+// be recorded into a capture and read back per replay); the events are destroyed when timing is switched off.
 struct Timing {
+  std::mutex mu;
   bool on = false;
   std::vector<cudaEvent_t> ev;   // start, stop, start, stop, ...
+  std::vector<uint8_t> fwd_only; // per event pair: 1 = scoring launch (forward only), 0 = guidance launch (fwd + dgrad)
+  std::vector<int64_t> pair_rows;
   size_t used = 0;
   int64_t rows = 0;
 };
@@ -852,14 +963,19 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   if (sm_counts[dev] == 0) {
     int n = 0;
     DGDM_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
-    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     sm_counts[dev] = n;
   }
   const int sm_count = sm_counts[dev];
-  Plan pl = make_plan(w, H1);
+  const Plan pl = make_plan(w, H1);
   TcParams P{};
-  P.img = (const uint8_t*)w->tc_image;
+  const bool f16 = precision == DGDM_PREC_FP16 || precision == DGDM_PREC_FP16X3;
+  // the image buffer holds the bf16 image followed by the fp16 image (dgdm_dyn_pack_tc writes both)
+  P.img = (const uint8_t*)w->tc_image + (f16 ? pl.bytes : 0);
+  P.gscale = f16 ? F16_GS : 1.f;
   P.U = U; P.Cst = Cst; P.Vt = V;
   for (int i = 0; i < 7; ++i) P.bias[i] = w->bl[i];
   P.w_out = w->w_out; P.b_out = w->b_out;
@@ -867,7 +983,7 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   P.part = part; P.score_part = score_part; P.logits = logits; P.err = err;
   P.obj = *obj;
   P.n_rows = n_rows; P.n_tiles = (int)n_tiles; P.G = G; P.H1 = H1; P.opd = opd; P.n_designs = n_designs; P.n_obj = n_obj;
-  P.x3 = precision == DGDM_PREC_BF16X3; P.backward = backward;
+  P.x3 = precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_FP16X3; P.backward = backward;
   // Segment list of this launch.  The image always holds the output-layer tile; the fp32-grade plan does not use
   // it: the last hidden layer becomes K_FOUT and the K_OUT segment is dropped.  Forward only stops after the output.
   int n_seg = 0;
@@ -884,20 +1000,29 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   DGDM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (g_timing.on) {
+  std::unique_lock<std::mutex> timing_lock(g_timing.mu);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (g_timing.on) DGDM_CUDA(cudaStreamIsCapturing(s, &cap));
+  if (g_timing.on && cap == cudaStreamCaptureStatusNone) {
     if (g_timing.used + 2 > g_timing.ev.size()) {
       for (int i = 0; i < 2; ++i) { cudaEvent_t e; DGDM_CUDA(cudaEventCreate(&e)); g_timing.ev.push_back(e); }
     }
     e0 = g_timing.ev[g_timing.used]; e1 = g_timing.ev[g_timing.used + 1];
     g_timing.used += 2; g_timing.rows += n_rows;
+    g_timing.fwd_only.push_back(backward ? 0 : 1);
+    g_timing.pair_rows.push_back(n_rows);
     DGDM_CUDA(cudaEventRecord(e0, s));
   }
-  if (P.x3) tc_trunk_kernel<true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
-  else tc_trunk_kernel<false><<<grid, NTHREADS, smem_bytes(), s>>>(P);
+  if (P.x3 && f16) tc_trunk_kernel<true, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
+  else if (P.x3) tc_trunk_kernel<true, false><<<grid, NTHREADS, smem_bytes(), s>>>(P);
+  else if (f16) tc_trunk_kernel<false, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
+  else tc_trunk_kernel<false, false><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   DGDM_LAUNCH_CHECK();
   if (e1) DGDM_CUDA(cudaEventRecord(e1, s));
+  timing_lock.unlock();
   if (backward) {
-    reduce_slots_kernel<<<(unsigned)((n_pairs * H1 + 255) / 256), 256, 0, s>>>(dUp, part, n_pairs, G, H1);
+    reduce_slots_kernel<<<(unsigned)((n_pairs * H1 + 255) / 256), 256, 0, s>>>(dUp, part, n_pairs, G, H1,
+                                                                               f16 ? 1.f / (F16_GS * F16_SW) : 1.f);
   } else {
     reduce_score_slots_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(score_sum, score_part, n_pairs, G);
   }
@@ -914,15 +1039,24 @@ extern "C" int dgdm_trunk_trace_read(long long* out, int32_t n) {
 #endif
 
 extern "C" int dgdm_trunk_timing(int32_t enable) {
-  dgdm::g_timing.on = enable != 0;
-  dgdm::g_timing.used = 0;
-  dgdm::g_timing.rows = 0;
+  using namespace dgdm;
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  g_timing.on = enable != 0;
+  g_timing.used = 0;
+  g_timing.rows = 0;
+  g_timing.fwd_only.clear();
+  g_timing.pair_rows.clear();
+  if (!g_timing.on) {
+    for (cudaEvent_t e : g_timing.ev) cudaEventDestroy(e);
+    g_timing.ev.clear();
+  }
   return DGDM_OK;
 }
 
 extern "C" int dgdm_trunk_timing_read(double* total_ms, int64_t* launches, int64_t* rows) {
   using namespace dgdm;
   DGDM_CHECK_ARG(total_ms && launches && rows, "dgdm_trunk_timing_read: null pointer");
+  std::lock_guard<std::mutex> lk(g_timing.mu);
   double tot = 0.0;
   for (size_t i = 0; i + 1 < g_timing.used; i += 2) {
     DGDM_CUDA(cudaEventSynchronize(g_timing.ev[i + 1]));
@@ -934,9 +1068,24 @@ extern "C" int dgdm_trunk_timing_read(double* total_ms, int64_t* launches, int64
   return DGDM_OK;
 }
 
+extern "C" int dgdm_trunk_timing_read_split(double* ms, int64_t* launches, int64_t* rows) {
+  using namespace dgdm;
+  DGDM_CHECK_ARG(ms && launches && rows, "dgdm_trunk_timing_read_split: null pointer");
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  for (int k = 0; k < 2; ++k) { ms[k] = 0.0; launches[k] = 0; rows[k] = 0; }
+  for (size_t i = 0; i + 1 < g_timing.used; i += 2) {
+    DGDM_CUDA(cudaEventSynchronize(g_timing.ev[i + 1]));
+    float t = 0.f;
+    DGDM_CUDA(cudaEventElapsedTime(&t, g_timing.ev[i], g_timing.ev[i + 1]));
+    const int k = g_timing.fwd_only[i / 2];
+    ms[k] += t; launches[k] += 1; rows[k] += g_timing.pair_rows[i / 2];
+  }
+  return DGDM_OK;
+}
+
 extern "C" size_t dgdm_dyn_tc_image_bytes(int32_t H1) {
   if (H1 != 256 && H1 != 512) return 0;
-  return dgdm::make_plan(nullptr, H1).bytes;
+  return 2 * dgdm::make_plan(nullptr, H1).bytes;          // bf16 image + fp16 image
 }
 
 extern "C" int dgdm_dyn_pack_tc(const dgdm_dyn_weights* w, void* tc_image, void* stream) {
@@ -945,10 +1094,13 @@ extern "C" int dgdm_dyn_pack_tc(const dgdm_dyn_weights* w, void* tc_image, void*
   DGDM_CHECK_ARG(w->H1 == 256 || w->H1 == 512, "dgdm_dyn_pack_tc: H1=%d unsupported", w->H1);
   DGDM_CHECK_ARG(((uintptr_t)tc_image) % 128 == 0, "dgdm_dyn_pack_tc: image must be 128-byte aligned");
   Plan pl = make_plan(w, w->H1);
-  for (int i = 0; i < pl.n_seg; ++i) {
-    const int chunks = 8 * pl.pack[i].n_rows * 8;
-    pack_tc_kernel<<<(chunks + 255) / 256, 256, 0, (cudaStream_t)stream>>>((uint8_t*)tc_image, pl.pack[i]);
-    DGDM_LAUNCH_CHECK();
+  for (int f16 = 0; f16 < 2; ++f16) {
+    for (int i = 0; i < pl.n_seg; ++i) {
+      const int chunks = 8 * pl.pack[i].n_rows * 8;
+      pack_tc_kernel<<<(chunks + 255) / 256, 256, 0, (cudaStream_t)stream>>>((uint8_t*)tc_image + (size_t)f16 * pl.bytes,
+                                                                            pl.pack[i], f16);
+      DGDM_LAUNCH_CHECK();
+    }
   }
   return DGDM_OK;
 }

@@ -196,10 +196,11 @@ extern "C" int dgdm_pointnet2_encode(const dgdm_pointnet2_weights* w, const floa
     const int nc = n_clouds - c0 < ncmax ? n_clouds - c0 : ncmax;
     const float* xyz0 = clouds + (int64_t)c0 * NPTS * 3;
     const int64_t* st = fps_start + (int64_t)c0 * 2;
-    // ---- sa1 ----
+    // ---- sa1 ----  (radius thresholds: `radius ** 2` in double, rounded once to fp32, as torch compares an fp32
+    // tensor with a Python scalar at pointnet2_utils.py:110)
     fps_kernel<<<nc, NPTS, 0, s>>>(xyz0, NPTS, 512, st, 2, W.fidx1, W.xyz1);
     DGDM_LAUNCH_CHECK();
-    ball_query_kernel<<<nb((int64_t)nc * 512, 128), 128, 0, s>>>(xyz0, NPTS, W.xyz1, 512, 0.2f * 0.2f, 32, W.gidx, (int64_t)nc * 512);
+    ball_query_kernel<<<nb((int64_t)nc * 512, 128), 128, 0, s>>>(xyz0, NPTS, W.xyz1, 512, (float)(0.2 * 0.2), 32, W.gidx, (int64_t)nc * 512);
     DGDM_LAUNCH_CHECK();
     int64_t rows = (int64_t)nc * 512 * 32;
     group_kernel<<<nb(rows * 3, 256), 256, 0, s>>>(W.g0, xyz0, nullptr, NPTS, 0, W.xyz1, W.gidx, 512, 32, rows);
@@ -211,7 +212,7 @@ extern "C" int dgdm_pointnet2_encode(const dgdm_pointnet2_weights* w, const floa
     // ---- sa2 ----
     fps_kernel<<<nc, NPTS, 0, s>>>(W.xyz1, 512, 128, st + 1, 2, W.fidx2, W.xyz2);
     DGDM_LAUNCH_CHECK();
-    ball_query_kernel<<<nb((int64_t)nc * 128, 128), 128, 0, s>>>(W.xyz1, 512, W.xyz2, 128, 0.4f * 0.4f, 64, W.gidx, (int64_t)nc * 128);
+    ball_query_kernel<<<nb((int64_t)nc * 128, 128), 128, 0, s>>>(W.xyz1, 512, W.xyz2, 128, (float)(0.4 * 0.4), 64, W.gidx, (int64_t)nc * 128);
     DGDM_LAUNCH_CHECK();
     rows = (int64_t)nc * 128 * 64;
     group_kernel<<<nb(rows * 131, 256), 256, 0, s>>>(W.g0, W.xyz1, W.f1, 512, 128, W.xyz2, W.gidx, 128, 64, rows);

@@ -640,8 +640,9 @@ extern "C" int dgdm_unet1d_forward(const dgdm_unet_weights* w, const float* x, i
                    "dgdm_unet1d_forward: block %d is %d->%d, expected %d->%d (train.py:80 configuration)", b,
                    w->blocks[b].cin, w->blocks[b].cout, kCin[b], kCout[b]);
   cudaStream_t s = (cudaStream_t)stream;
-  DGDM_CHECK_ARG(precision == DGDM_PREC_FP32_SIMT || precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_BF16,
-                 "dgdm_unet1d_forward: unknown precision %d", precision);
+  DGDM_CHECK_ARG(precision == DGDM_PREC_FP32_SIMT || precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_BF16 ||
+                     precision == DGDM_PREC_FP16 || precision == DGDM_PREC_FP16X3, "dgdm_unet1d_forward: unknown precision %d", precision);
+  if (precision == DGDM_PREC_FP16 || precision == DGDM_PREC_FP16X3) precision = DGDM_PREC_BF16X3;   // the fp16 mode is a trunk mode; the denoiser stays fp32-grade
   if (precision != DGDM_PREC_FP32_SIMT) return unet_forward_tc(w, x, n, P, t, eps, workspace, workspace_bytes, precision, s);
   const int L = P, L2 = P / 2, R = L + 4, R2 = L2 + 4;
   const int64_t nc = n < CHUNK ? n : CHUNK;

@@ -169,6 +169,7 @@ class Diffusion:
         self.threshold = torch.tensor(thr)
         self.std = torch.tensor(std)
         self.threshold_std = self.threshold / self.std
+        self.max_designs_per_launch = 131072                     # guided_sample chunks objects beyond this (see there)
         self._ws: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, tuple] = {}                    # captured passes (guided_sample(cuda_graph=True))
         self._obj_version = 0                                    # bumped by set_objects: captured graphs read its buffers
@@ -208,7 +209,7 @@ class Diffusion:
         ws = self._workspace("pn2", nb)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dgdm_pointnet2_encode(C.byref(self.pn2.struct), ov.data_ptr(), n, npts, st.data_ptr(),
-                                                      codes.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
+                                                      codes.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)),
                        "dgdm_pointnet2_encode")
         return codes
 
@@ -237,9 +238,19 @@ class Diffusion:
         ws = self._workspace("unet", self.lib.dgdm_unet1d_workspace_bytes(n, P))
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dgdm_unet1d_forward(C.byref(self.unet.struct), x.data_ptr(), n, P, t, eps.data_ptr(),
-                                                    ws.data_ptr(), ws.numel(), self.precision, _lib.stream_ptr()),
+                                                    ws.data_ptr(), ws.numel(), self.precision, _lib.stream_ptr(self.device)),
                        "dgdm_unet1d_forward")
         return eps.reshape(sample.shape)
+
+    def _check_widths(self, x: torch.Tensor, objects_dev: torch.Tensor) -> None:
+        """The C ABI takes P and obj_dim from the weight struct: a tensor of another width would be read with the
+        wrong stride (or out of bounds), so refuse it here."""
+        if x.dim() != 2 or x.shape[1] != self.dyn.P:
+            raise ValueError(f"designs must be (n, {self.dyn.P}), got {tuple(x.shape)}")
+        if objects_dev.dim() != 2 or objects_dev.shape[1] != self.dyn.obj_dim:
+            raise ValueError(f"objects must be (n, {self.dyn.obj_dim}) "
+                             f"({'PointNet++ codes' if self.dyn.is_3d else 'flattened contours'}), "
+                             f"got {tuple(objects_dev.shape)}")
 
     def _grid(self, ori_range: Sequence[float], profile: bool = False) -> _lib.PoseGrid:
         g = _lib.PoseGrid()
@@ -255,6 +266,7 @@ class Diffusion:
                  ori_range=(-1.0, 1.0), grad_mul: float = 1.0, row_coef: Optional[torch.Tensor] = None,
                  pair_object: Optional[torch.Tensor] = None, want_logits: bool = False):
         """Batched cond_fn: x (n_designs,P) -> grad (n_designs,P) [, logits (n_pairs*G,3)]."""
+        self._check_widths(x, objects_dev)
         nd, P = x.shape
         n_obj = objects_dev.shape[0]
         grid = self._grid(ori_range)
@@ -269,7 +281,7 @@ class Diffusion:
             _lib.check(self.lib.dgdm_dyn_guidance(
                 C.byref(self.dyn.struct), x.data_ptr(), nd, objects_dev.data_ptr(), n_obj, objs_per_design,
                 _lib.ptr(pair_object), self._t_frac(t), C.byref(grid), C.byref(obj), float(grad_mul), grad.data_ptr(),
-                _lib.ptr(logits), ws.data_ptr(), ws.numel(), self.precision, _lib.stream_ptr()), "dgdm_dyn_guidance")
+                _lib.ptr(logits), ws.data_ptr(), ws.numel(), self.precision, _lib.stream_ptr(self.device)), "dgdm_dyn_guidance")
         return (grad, logits) if want_logits else grad
 
     def score(self, x: torch.Tensor, objects_dev: torch.Tensor, objs_per_design: int, opt_obj: str,
@@ -277,6 +289,7 @@ class Diffusion:
         """Predicted task score per (design, object) pair: mean objective over the ``grid_size`` profile
         orientations at t = 0, pos = (0,0) -- the input convention of get_convergence_centers
         (diffusion.py:509-516)."""
+        self._check_widths(x, objects_dev)
         nd, P = x.shape
         n_obj = objects_dev.shape[0]
         grid = self._grid(ori_range, profile=True)
@@ -291,7 +304,7 @@ class Diffusion:
             _lib.check(self.lib.dgdm_dyn_score(
                 C.byref(self.dyn.struct), x.data_ptr(), nd, objects_dev.data_ptr(), n_obj, objs_per_design, None,
                 self._t_frac(t), C.byref(grid), C.byref(obj), scores.data_ptr(), _lib.ptr(logits), ws.data_ptr(),
-                ws.numel(), self.precision, _lib.stream_ptr()), "dgdm_dyn_score")
+                ws.numel(), self.precision, _lib.stream_ptr(self.device)), "dgdm_dyn_score")
         return (scores, logits) if want_logits else scores
 
     def classifier_model(self, pts: torch.Tensor, ori: torch.Tensor, pos: torch.Tensor, timesteps: torch.Tensor,
@@ -319,7 +332,10 @@ class Diffusion:
             if object_vertices is None:
                 raise ValueError("object vertices not provided")
             objs = f(object_vertices.reshape(object_vertices.shape[0], -1))
+        self._check_widths(x, objs)
         n = x.shape[0]
+        if objs.shape[0] != n:
+            raise ValueError(f"classifier_model: {objs.shape[0]} object rows for {n} design rows")
         o, p, t = f(ori.reshape(n)), f(pos.reshape(n, 2)), f(timesteps.reshape(n))
         logits = torch.empty((n, 3), dtype=torch.float32, device=self.device)
         grad = torch.empty_like(x) if return_grad else None
@@ -331,7 +347,7 @@ class Diffusion:
             _lib.check(self.lib.dgdm_dyn_forward_rows(
                 C.byref(self.dyn.struct), x.data_ptr(), o.data_ptr(), p.data_ptr(), t.data_ptr(), objs.data_ptr(), n,
                 C.byref(obj) if obj is not None else None, logits.data_ptr(), _lib.ptr(grad), ws.data_ptr(), ws.numel(),
-                self.precision, _lib.stream_ptr()), "dgdm_dyn_forward_rows")
+                self.precision, _lib.stream_ptr(self.device)), "dgdm_dyn_forward_rows")
         return (logits, grad) if return_grad else logits
 
     def best_of_n(self, scores: torch.Tensor, k: int = 1):
@@ -342,7 +358,7 @@ class Diffusion:
         best = torch.empty((n_obj, k), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dgdm_best_of_n(s.data_ptr(), n_obj, n_cand, k, idx.data_ptr(), best.data_ptr(),
-                                               _lib.stream_ptr()), "dgdm_best_of_n")
+                                               _lib.stream_ptr(self.device)), "dgdm_best_of_n")
         return idx, best
 
     # ------------------------------------------------------------------------------------------
@@ -421,14 +437,16 @@ class Diffusion:
             static_in = nz.clone()
             body(static_in)                                      # eager warm-up
             torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                static_out = body(static_in)
+            with torch.cuda.device(self.device):             # capture on the device that owns the buffers
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    static_out = body(static_in)
             ent = (g, static_in, static_out, dict(self._ws))     # keep the captured workspaces alive if the cache regrows
             self._graphs[key] = ent
         g, static_in, static_out = ent[:3]
         static_in.copy_(nz)
-        g.replay()
+        with torch.cuda.device(self.device):
+            g.replay()
         return {k: v.clone() for k, v in static_out.items()}
 
     def _check_noise(self, noise: torch.Tensor, batch_size: int) -> torch.Tensor:
@@ -455,9 +473,10 @@ class Diffusion:
         a = self.noise_scheduler.alphas_cumprod[self.num_inference_steps]
         # add_noise: sqrt(a) x0 + sqrt(1-a) eps  ==  K4 with an identity x0 stage (sqrt_1m_at = 0, sqrt_at = 1, no clip)
         sample = torch.empty_like(data)
-        _lib.check(self.lib.dgdm_ddim_guided_update(sample.data_ptr(), data.data_ptr(), noise.data_ptr(), None, data.numel(),
-                                                    0.0, 1.0, float(a ** 0.5), float((1 - a) ** 0.5), 0.0, 0,
-                                                    _lib.stream_ptr()), "dgdm_ddim_guided_update")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dgdm_ddim_guided_update(sample.data_ptr(), data.data_ptr(), noise.data_ptr(), None,
+                                                        data.numel(), 0.0, 1.0, float(a ** 0.5), float((1 - a) ** 0.5),
+                                                        0.0, 0, _lib.stream_ptr(self.device)), "dgdm_ddim_guided_update")
         npl = 0.0
         for t in self.noise_scheduler.timesteps.tolist():
             eps = self.noise_pred_net(sample, t)
@@ -492,9 +511,15 @@ class Diffusion:
                 batch_idx, batch_size, nz, save_dir, opt_obj, ori_range, None, top_k))
         n_obj = self._obj_dev.shape[0]
         B, P = batch_size, self.num_points
-        scale = self.classifier_scale(opt_obj)
         x0 = self._check_noise(noise, B)
-        x = x0.repeat(n_obj, 1).contiguous()                     # design d = o*B + b (object-major)
+        # Bound the per-launch working set: the guidance kernel keeps one H1-wide partial sum per (pair, tile) in its
+        # workspace (~20 KB per design at G = 1125), so a 1024-object x 512-candidate sweep on one GPU would ask for
+        # 10 GB.  Objects are independent (diffusion.py:561-570), so chunks of objects give identical results.
+        per_launch = max(1, self.max_designs_per_launch // B)
+        if n_obj > per_launch and opt_obj != "convergence" and trace is None:
+            parts = [self._guided_sample_objects(self._obj_dev[o:o + per_launch], x0, opt_obj, ori_range, None, top_k, None)
+                     for o in range(0, n_obj, per_launch)]
+            return {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
         row_coef = None
         if opt_obj == "convergence":
             if unguided_sample is None:
@@ -504,16 +529,25 @@ class Diffusion:
             row_coef = torch.cat([self._convergence_row_coef(
                 self.get_convergence_centers(unguided_sample, self.object_vertices[o], B, ori_range), B)
                 for o in range(n_obj)])
+        return self._guided_sample_objects(self._obj_dev, x0, opt_obj, ori_range, row_coef, top_k, trace)
+
+    def _guided_sample_objects(self, obj_dev: torch.Tensor, x0: torch.Tensor, opt_obj: str, ori_range, row_coef,
+                               top_k: int, trace: Optional[list]) -> Dict[str, torch.Tensor]:
+        """The step loop of guided_sample (diffusion.py:570-576) for the objects in ``obj_dev``, all at once."""
+        n_obj = obj_dev.shape[0]
+        B, P = x0.shape
+        scale = self.classifier_scale(opt_obj)
+        x = x0.repeat(n_obj, 1).contiguous()                     # design d = o*B + b (object-major)
         for t in self.noise_scheduler.timesteps.tolist():
             eps = self.noise_pred_net(x, t)
-            grad = self.guidance(x, t, self._obj_dev, 1, opt_obj, ori_range, 1.0, row_coef)
+            grad = self.guidance(x, t, obj_dev, 1, opt_obj, ori_range, 1.0, row_coef)
             nxt = self.noise_scheduler.guided_step(eps, t, x, grad, scale)
             if trace is not None:
                 trace.append(dict(t=t, eps=eps.reshape(n_obj, B, P, 1), grad=grad.reshape(n_obj, B, P, 1),
                                   sample=nxt.reshape(n_obj, B, P, 1)))
             x = nxt
         score_obj = "rotate_counterclockwise" if opt_obj == "convergence" else opt_obj
-        scores = self.score(x, self._obj_dev, 1, score_obj, ori_range).reshape(n_obj, B)
+        scores = self.score(x, obj_dev, 1, score_obj, ori_range).reshape(n_obj, B)
         idx, best = self.best_of_n(scores, top_k)
         return {"designs": x.reshape(n_obj, B, P, 1), "scores": scores, "best_ids": idx, "best_scores": best}
 

@@ -2,9 +2,17 @@
 
 (object, candidate) pairs are independent in ``guided_sample`` (generator/diffusion.py:561-570: every object
 restarts from the same noise; no BatchNorm batch statistics in eval mode), so per-object mode shards OBJECTS
-contiguously across ranks and nothing crosses NVLink until the final scores / designs are gathered for the
-best-of-N table.  Multi-object mode averages gradients over objects per candidate
-(:640-644), so it shards CANDIDATES and keeps every object on every rank -- still no per-step traffic.
+contiguously across ranks when there are at least as many objects as ranks, and CANDIDATES otherwise (the stock 3D
+set is 5 objects, assets/object_names_test.txt: on 8 GPUs an object split would idle three of them); nothing crosses
+NVLink until the final scores / designs are gathered for the best-of-N table.  Multi-object mode
+averages gradients over objects per candidate (:640-644), so it always shards CANDIDATES and keeps every object on
+every rank -- still no per-step traffic.
+
+Bit-exactness across world sizes: a design's trajectory does not depend on its neighbours in the batch, and the
+guidance kernel sums a (design, object) pair's pose rows in 128-row tiles that are aligned to the START OF THE
+BATCH.  An object shard therefore reproduces the 1-rank result bit for bit whenever candidates x pose rows is a
+multiple of 128 (every BASELINE configuration: 256 x 900, 128 x 1125, 512 x 1125); a candidate shard changes the tile
+alignment of a pair and agrees to fp32 reassociation (~1e-6 relative) instead.
 
 The reference's own multi-GPU story is ``nn.DataParallel`` row scatter per cond_fn call (generator/train.py:86)
 plus duplicated DDP validation; it is not a model to follow.
@@ -55,6 +63,55 @@ def gather_per_object_results(local: Dict[str, torch.Tensor], n_obj_global: int,
     if gather_designs:
         out["designs"] = all_gather_ragged(local["designs"], sizes, group)
     return out
+
+
+def plan_per_object(n_obj: int, world: int) -> str:
+    """'objects' when every rank can own at least one whole object, else 'candidates' (SURVEY.md §8e)."""
+    return "objects" if n_obj >= world else "candidates"
+
+
+def gather_per_object_candidate_shards(local: Dict[str, torch.Tensor], batch_global: int, top_k: int, select_fn,
+                                       group=None, gather_designs: bool = True) -> Dict[str, torch.Tensor]:
+    """Per-object mode with CANDIDATES sharded (fewer objects than ranks): ``local`` holds every object with this
+    rank's candidate slice -- scores (n_obj, B_local), designs (n_obj, B_local, P, 1).  Gathers along the candidate axis
+    (rank-major == global candidate order) and re-runs the selection on the full (n_obj, B) table on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    sizes = shard_sizes(batch_global, dist.get_world_size(group))
+    scores = all_gather_ragged(local["scores"].transpose(0, 1).contiguous(), sizes, group).transpose(0, 1).contiguous()
+    idx, best = select_fn(scores, top_k)
+    out = {"scores": scores, "best_ids": idx, "best_scores": best}
+    if gather_designs:
+        out["designs"] = all_gather_ragged(local["designs"].transpose(0, 1).contiguous(), sizes, group).transpose(0, 1).contiguous()
+    return out
+
+
+def sharded_guided_sample(build_dm, objects: torch.Tensor, fps_starts: Optional[torch.Tensor], noise: torch.Tensor,
+                          opt_obj: str, top_k: int = 1, gather_designs: bool = True, group=None, dm=None,
+                          **sample_kwargs) -> Dict[str, torch.Tensor]:
+    """Per-object guided sampling of a GLOBAL object set on every rank of ``group``; every rank returns the same global
+    tables (scores (n_obj,B), best_ids (n_obj,k), best_scores [, designs (n_obj,B,P,1)]).
+
+    ``build_dm(objects_shard, fps_shard, object_ids) -> Diffusion`` builds this rank's sampler (pass ``dm`` to reuse
+    one built for the same shard).  Objects are sharded when ``n_obj >= world``, candidates otherwise."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    n_obj, B = objects.shape[0], noise.shape[0]
+    if plan_per_object(n_obj, world) == "objects":
+        lo, hi = shard_range(n_obj, world, rank)
+        if dm is None:
+            dm = build_dm(objects[lo:hi], None if fps_starts is None else fps_starts[lo:hi], list(range(lo, hi)))
+        local = dm.guided_sample(0, B, noise, opt_obj=opt_obj, top_k=top_k, **sample_kwargs)
+        return gather_per_object_results(local, n_obj, group, gather_designs=gather_designs)
+    lo, hi = shard_range(B, world, rank)
+    if dm is None:
+        dm = build_dm(objects, fps_starts, list(range(n_obj)))
+    if hi == lo:                                                        # more ranks than candidates: nothing to do here
+        P = noise.shape[1]
+        local = {"scores": torch.empty((n_obj, 0), device=dm.device), "designs": torch.empty((n_obj, 0, P, 1), device=dm.device)}
+    else:
+        local = dm.guided_sample(0, hi - lo, noise[lo:hi], opt_obj=opt_obj, top_k=min(top_k, hi - lo), **sample_kwargs)
+    return gather_per_object_candidate_shards(local, B, top_k, dm.best_of_n, group, gather_designs=gather_designs)
 
 
 def gather_multi_object_results(local: Dict[str, torch.Tensor], batch_global: int, top_k: int, select_fn,

@@ -2,8 +2,9 @@
 (dynamics/sim_test_mj.py -> dynamics/metrics.py:metric2objective -> generator/diffusion.py:391-428); the simulator
 is CPU-only and out of scope, so this module builds the same tables from the dynamics network's own profile pass
 (logits of ``Diffusion.profile_logits``), with the reference's thresholds, units, key names and arg-min/max rules,
-so the GPU best-of-N is a like-for-like stand-in.  Keys that only a roll-out can produce (``final_*``,
-``max_convergence_range_*``) are not emitted.
+so the GPU best-of-N is a like-for-like stand-in.  Keys that only a roll-out can produce (``final_*``) appear when
+the caller supplies the simulator's ``final_*`` fields (then the tables are the reference's key for key: pinned by
+tests/test_metrics_golden.py against the reference's own functions); ``max_convergence_range_*`` is not emitted.
 
 Also ``export_designs``: de-normalise control points to the metres the simulators consume.
 """
@@ -44,11 +45,18 @@ _TRN = {("x", 0): "up", ("x", 2): "down", ("y", 0): "left", ("y", 2): "right"}
 
 
 def metric2objective(metric: Dict[str, np.ndarray], objective: str) -> Dict[str, float]:
-    """Predicted analogue of dynamics/metrics.py:67-233 for one candidate (metric fields are (n_rot,) arrays)."""
+    """dynamics/metrics.py:67-233 for one candidate (metric fields are (n_rot,) arrays): same keys, in the same order,
+    same dtypes (class counts are ints, rates and means floats).  The roll-out keys (``final_delta_theta[_abs]``,
+    ``final_pos_x|y``) are emitted when the metric dict carries the simulator's ``final_*`` fields and left out for a
+    prediction-only dict (``predicted_metrics``)."""
     p, px, py = metric["profile"], metric["profile_x"], metric["profile_y"]
+    has_final = "final_delta_theta" in metric
     if objective in ("rotate", "rotate_in_place"):
-        return {"success_rate": float(np.mean((p == 0) | (p == 2), dtype=np.float32)),
-                "num_zero_classes": int(np.sum(p == 1)), "delta_theta_abs": float(np.mean(np.abs(metric["delta_theta"])))}
+        out = {"success_rate": float(np.mean((p == 0) | (p == 2), dtype=np.float32)),
+               "num_zero_classes": int(np.sum(p == 1)), "delta_theta_abs": float(np.mean(np.abs(metric["delta_theta"])))}
+        if has_final:
+            out["final_delta_theta_abs"] = float(np.mean(np.abs(metric["final_delta_theta"])))
+        return out
     if objective not in _SPEC:
         raise ValueError("opt obj not supported")
     rot, axis, trn = _SPEC[objective]
@@ -67,9 +75,14 @@ def metric2objective(metric: Dict[str, np.ndarray], objective: str) -> Dict[str,
     if rot is not None:
         out[f"num_{_ROT[rot]}_classes"] = n_rot
         out["delta_theta"] = float(np.mean(metric["delta_theta"]))
+        if has_final:
+            out["final_delta_theta"] = float(np.mean(metric["final_delta_theta"]))
     if axis is not None:
+        col = 0 if axis == "x" else 1
         out[f"num_{_TRN[(axis, trn)]}_classes"] = n_trn
-        out["delta_pos_" + axis] = float(np.mean(metric["delta_pos"][..., 0 if axis == "x" else 1]))
+        out["delta_pos_" + axis] = float(np.mean(metric["delta_pos"][..., col]))
+        if "final_pos" in metric:
+            out["final_pos_" + axis] = float(np.mean(np.asarray(metric["final_pos"])[..., col]))
     return out
 
 
@@ -77,25 +90,51 @@ def _direction(key: str, objective: str) -> str:
     """arg-min or arg-max per key, as generator/diffusion.py:391-428."""
     if key == "num_zero_classes":
         return "min"
-    if key.startswith("num_") or key in ("success_rate", "delta_theta_abs"):
+    if key.startswith("num_") or key in ("success_rate", "delta_theta_abs", "final_delta_theta_abs"):
         return "max"
     rot, axis, trn = _SPEC[objective]
-    if key == "delta_theta":
+    if key in ("delta_theta", "final_delta_theta"):
         return "min" if rot == 0 else "max"              # clockwise = negative d_theta
-    if key in ("delta_pos_x", "delta_pos_y"):
+    if key in ("delta_pos_x", "delta_pos_y", "final_pos_x", "final_pos_y"):
         return "min" if trn == 0 else "max"              # up / left = negative
     raise KeyError(key)
 
 
-def get_best_ids_all_metrics(objectives: Sequence[Dict[str, float]], opt_obj: str = "rotate") -> Dict[str, int]:
-    """Index of the best candidate per metric key, first occurrence on ties (np.argmax / np.argmin)."""
+def _check_objective(opt_obj: str) -> None:
     if opt_obj not in _SPEC and opt_obj not in ("rotate", "rotate_in_place"):
-        raise ValueError("opt obj not supported")
+        raise ValueError("opt obj not supported")        # generator/diffusion.py:388,425
+
+
+def get_best_ids_all_metrics(objectives: Sequence[Dict[str, float]], opt_obj: str = "rotate") -> Dict[str, int]:
+    """generator/diffusion.py:391-428: index of the best candidate per metric key, first occurrence on ties
+    (np.argmax / np.argmin); keys in the reference's order, ``success_rate`` last."""
+    _check_objective(opt_obj)
     best = {}
-    for key in objectives[0]:
+    for key in [k for k in objectives[0] if k != "success_rate"] + ["success_rate"]:
         vals = np.asarray([o[key] for o in objectives])
         best[key] = int(np.argmin(vals) if _direction(key, opt_obj) == "min" else np.argmax(vals))
     return best
+
+
+def get_average_best_ids(objectives: Sequence[Dict[str, float]], opt_obj: str = "rotate") -> int:
+    """generator/diffusion.py:354-389: the single ranking key of each objective -- fewest in-threshold classes for
+    'rotate', the most classes of the wanted kind otherwise (the combined count for the 8 combination objectives)."""
+    _check_objective(opt_obj)
+    if opt_obj in ("rotate", "rotate_in_place"):
+        return int(np.argmin([o["num_zero_classes"] for o in objectives]))
+    rot, axis, trn = _SPEC[opt_obj]
+    name = "_".join(([_ROT[rot]] if rot is not None else []) + ([_TRN[(axis, trn)]] if axis is not None else []))
+    return int(np.argmax([o[f"num_{name}_classes"] for o in objectives]))
+
+
+def get_best_ids(objectives: Sequence[Dict[str, float]], num_grippers: int, num_objects: int,
+                 opt_obj: str = "rotate") -> List[Dict[str, int]]:
+    """generator/diffusion.py:346-352: per-object blocks of ``num_grippers`` candidates, ids offset by the block start."""
+    out = []
+    for idx in range(num_objects):
+        best = get_best_ids_all_metrics(objectives[idx * num_grippers:(idx + 1) * num_grippers], opt_obj)
+        out.append({k: v + idx * num_grippers for k, v in best.items()})
+    return out
 
 
 def predicted_objectives(logits: np.ndarray, opt_obj: str, mode: str = "point") -> List[Dict[str, float]]:

@@ -198,8 +198,9 @@ class DynamicsPack:
         l = _lib.lib()
         n = l.dgdm_dyn_tc_image_bytes(self.H1)
         self.tc_image = torch.empty(n, dtype=torch.uint8, device=self.device)
-        _lib.check(l.dgdm_dyn_pack_tc(C.byref(self.struct), self.tc_image.data_ptr(), _lib.stream_ptr()),
-                   "dgdm_dyn_pack_tc")
+        with torch.cuda.device(self.device):
+            _lib.check(l.dgdm_dyn_pack_tc(C.byref(self.struct), self.tc_image.data_ptr(), _lib.stream_ptr(self.device)),
+                       "dgdm_dyn_pack_tc")
         self.struct.tc_image = self.tc_image.data_ptr()
 
 
@@ -240,6 +241,6 @@ class UnetPack:
         n = l.dgdm_unet_tc_image_bytes(C.byref(self.struct))
         self.tc_image = torch.empty(n, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(l.dgdm_unet_pack_tc(C.byref(self.struct), self.tc_image.data_ptr(), _lib.stream_ptr()),
+            _lib.check(l.dgdm_unet_pack_tc(C.byref(self.struct), self.tc_image.data_ptr(), _lib.stream_ptr(self.device)),
                        "dgdm_unet_pack_tc")
         self.struct.tc_image = self.tc_image.data_ptr()

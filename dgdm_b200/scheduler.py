@@ -56,10 +56,13 @@ class DDIMScheduler:
         c = self.coefficients(t)
         out = torch.empty_like(sample) if out is None else out
         l = _lib.lib()
-        _lib.check(l.dgdm_ddim_guided_update(_lib.ptr(out), _lib.ptr(sample), _lib.ptr(eps), _lib.ptr(grad),
-                                             sample.numel(), c[0], c[1], c[2], c[3], float(scale),
-                                             int(bool(self.config.clip_sample)), _lib.stream_ptr()),
-                   "dgdm_ddim_guided_update")
+        # launch in the context (and on the current stream) of the device that owns the tensors, whatever the
+        # process-wide current device is
+        with torch.cuda.device(sample.device):
+            _lib.check(l.dgdm_ddim_guided_update(_lib.ptr(out), _lib.ptr(sample), _lib.ptr(eps), _lib.ptr(grad),
+                                                 sample.numel(), c[0], c[1], c[2], c[3], float(scale),
+                                                 int(bool(self.config.clip_sample)), _lib.stream_ptr(sample.device)),
+                       "dgdm_ddim_guided_update")
         return out
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor):

@@ -39,7 +39,13 @@ enum {
 enum {
   DGDM_PREC_FP32_SIMT = 0, /* fp32 FFMA on CUDA cores: exact-order reference path on the GPU            */
   DGDM_PREC_BF16X3 = 1,    /* tcgen05 kind::f16, operands split hi+lo bf16, 3 MMAs: fp32-grade (<=1e-3)  */
-  DGDM_PREC_BF16 = 2       /* tcgen05 kind::f16, single bf16 pass (<=2e-2)                               */
+  DGDM_PREC_BF16 = 2,      /* tcgen05 kind::f16, single bf16 pass (<=2e-2)                               */
+  DGDM_PREC_FP16 = 3,      /* tcgen05 kind::f16, single fp16 pass in the trunk (3 more mantissa bits than bf16, same
+                            * tensor rate); the denoiser runs in BF16X3                                          */
+  DGDM_PREC_FP16X3 = 4     /* as BF16X3 with fp16 hi+lo operand parts in the trunk (22 operand bits instead of 16, same
+                            * 3 MMAs per product); the denoiser runs in BF16X3.  Both fp16 modes keep operands scaled
+                            * by powers of two inside the kernel (weights x256, activations x64, gradients x64) and
+                            * saturate: |BN-folded weight| < 255 and |activation| < 1023 are assumed               */
 };
 
 const char* dgdm_last_error(void);
@@ -118,8 +124,8 @@ typedef struct dgdm_objective {
 
 /* Size in bytes of the tensor-core weight image for a network with layer-1 width H1. */
 size_t dgdm_dyn_tc_image_bytes(int32_t H1);
-/* Build the image (bf16 hi/lo split, 64-wide K blocks, 128B-swizzled K-major tiles ready for
- * cp.async.bulk + tcgen05.mma) from the fp32 fields of *w into tc_image (device). */
+/* Build the image (a bf16 hi/lo copy followed by an fp16 hi/lo copy; 64-wide K blocks, 128B-swizzled K-major
+ * tiles ready for cp.async.bulk + tcgen05.mma) from the fp32 fields of *w into tc_image (device). */
 int dgdm_dyn_pack_tc(const dgdm_dyn_weights* w, void* tc_image, void* stream);
 
 size_t dgdm_dyn_guidance_workspace_bytes(const dgdm_dyn_weights* w, int32_t n_designs, int32_t n_obj,
@@ -170,6 +176,10 @@ int dgdm_dyn_forward_rows(const dgdm_dyn_weights* w, const float* x, const float
  * of launches and the number of guidance rows they processed. */
 int dgdm_trunk_timing(int32_t enable);
 int dgdm_trunk_timing_read(double* total_ms, int64_t* launches, int64_t* rows);
+/* The same, split by launch kind: index 0 = guidance launches (forward + input-gradient), index 1 = scoring
+ * launches (forward only).  ms, launches, rows each point at two elements.  Launches made while their stream is
+ * being captured into a CUDA graph are not timed. */
+int dgdm_trunk_timing_read_split(double* ms, int64_t* launches, int64_t* rows);
 
 /* ------------------------------------------------------------------------------------------------
  * K3  denoiser.  Replaces ConditionalUnet1D.forward (generator/diffusion_utils.py:238-285) for the one

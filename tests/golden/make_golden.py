@@ -14,9 +14,11 @@ restatement of diffusers==0.11.1 (not installable offline) -- that arithmetic is
 Weights and inputs come from dgdm_b200.synthetic (numpy RandomState => reproducible anywhere), and
 are loaded into the reference modules with strict=True, which also validates the name/shape tables.
 
-    python tests/golden/make_golden.py        # rewrites tests/golden/*.npz
+    python tests/golden/make_golden.py            # rewrites tests/golden/golden_{2d,3d}.npz
+    python tests/golden/make_golden.py bigG       # golden_bigG.npz: cond_fn at BASELINE pose-grid sizes (G = 900 / 1125)
+    python tests/golden/make_golden.py metrics    # golden_metrics.json: metric2objective / get_best_ids_* tables
 """
-import math
+import json
 import os
 import sys
 import types
@@ -32,97 +34,16 @@ sys.path.insert(0, REPO)
 
 
 # ---------------------------------------------------------------------------------------------
-# third-party stubs
+# third-party stubs: shared with bench.py's reference arm (oracle/ref_stubs.py)
 # ---------------------------------------------------------------------------------------------
-class _StubDDIM:
-    """diffusers==0.11.1 DDIMScheduler(num_train_timesteps, 'squaredcos_cap_v2', clip_sample=True,
-    prediction_type='epsilon'), eta=0 -- restated, see module docstring."""
+sys.path.insert(0, os.path.join(REPO, "oracle"))
+import ref_stubs  # noqa: E402
 
-    class _Cfg:
-        pass
-
-    class _Out:
-        def __init__(self, prev_sample):
-            self.prev_sample = prev_sample
-
-    def __init__(self, num_train_timesteps, beta_schedule="squaredcos_cap_v2", clip_sample=True,
-                 prediction_type="epsilon"):
-        assert beta_schedule == "squaredcos_cap_v2" and prediction_type == "epsilon"
-        self.config = self._Cfg()
-        self.config.num_train_timesteps = num_train_timesteps
-        self.config.clip_sample = clip_sample
-        bar = lambda s: math.cos((s + 0.008) / 1.008 * math.pi / 2) ** 2
-        T = num_train_timesteps
-        betas = torch.tensor([min(1 - bar((i + 1) / T) / bar(i / T), 0.999) for i in range(T)], dtype=torch.float32)
-        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
-        self.final_alpha_cumprod = torch.tensor(1.0)
-        self.num_inference_steps = None
-        self.timesteps = torch.from_numpy(np.arange(0, T)[::-1].copy().astype(np.int64))
-
-    def set_timesteps(self, n):
-        self.num_inference_steps = n
-        ratio = self.config.num_train_timesteps // n
-        self.timesteps = torch.from_numpy((np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64))
-
-    def step(self, model_output, timestep, sample):
-        prev = timestep - self.config.num_train_timesteps // self.num_inference_steps
-        a_t = self.alphas_cumprod[timestep]
-        a_p = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
-        b_t = 1 - a_t
-        x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
-        if self.config.clip_sample:
-            x0 = torch.clamp(x0, -1, 1)
-        std = 0.0 * ((1 - a_p) / (1 - a_t) * (1 - a_t / a_p)) ** 0.5
-        direction = (1 - a_p - std ** 2) ** 0.5 * model_output
-        return self._Out(a_p ** 0.5 * x0 + direction)
+_StubDDIM = ref_stubs.StubDDIM
 
 
 def install_stubs():
-    def mod(name, **attrs):
-        m = types.ModuleType(name)
-        m.__dict__.update(attrs)
-        sys.modules[name] = m
-        return m
-
-    mod("matplotlib").pyplot = mod("matplotlib.pyplot")
-
-    class LightningModule(nn.Module):
-        @property
-        def device(self):
-            return torch.device("cpu")
-
-        def log(self, *a, **k):
-            pass
-
-        def log_dict(self, *a, **k):
-            pass
-
-    mod("pytorch_lightning", LightningModule=LightningModule)
-
-    class _EMA:
-        def __init__(self, *a, **k):
-            pass
-
-    d = mod("diffusers", UNet2DModel=type("UNet2DModel", (), {}))
-    d.schedulers = mod("diffusers.schedulers")
-    mod("diffusers.schedulers.scheduling_ddim", DDIMScheduler=_StubDDIM, DDIMSchedulerOutput=_StubDDIM._Out)
-    mod("diffusers.schedulers.scheduling_ddpm", DDPMScheduler=type("DDPMScheduler", (), {}),
-        DDPMSchedulerOutput=type("DDPMSchedulerOutput", (), {}))
-    mod("diffusers.training_utils", EMAModel=_EMA)
-
-    def _no_sim(*a, **k):
-        raise RuntimeError("MuJoCo evaluator is out of scope")
-
-    # the real `dynamics` package must stay importable, only these two modules are stubbed
-    sys.path.insert(0, REF)
-    import dynamics  # noqa: F401  (namespace package under /root/reference)
-    mod("dynamics.sim_test_mj", sim_test_batch=_no_sim)
-    mod("dynamics.sim_test_mj_3d", sim_test_batch_3d=_no_sim)
-    if "wandb" not in sys.modules:
-        try:
-            import wandb  # noqa: F401
-        except Exception:
-            mod("wandb")
+    ref_stubs.install_stubs(REF)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -332,5 +253,125 @@ def main():
     print("golden_3d.npz:", len(out3), "arrays")
 
 
+# ---------------------------------------------------------------------------------------------
+def _build(mode, grid, npos, objs, sub_bs=16, seed=0):
+    """The reference's Diffusion module around the reference's real networks, synthetic weights (strict load)."""
+    from generator.diffusion import Diffusion
+    from generator.diffusion_utils import ConditionalUnet1D
+    from dynamics.profile_forward_2d import ProfileForward2DModel
+    from dynamics.profile_forward_3d import ProfileForward3DModel
+    from dgdm_b200 import synthetic as syn
+    P = 14 if mode == "point" else 42
+    unet = ConditionalUnet1D(input_dim=1, global_cond_dim=0, down_dims=[128, 256], diffusion_step_embed_dim=32)
+    unet.load_state_dict(syn.unet1d_state_dict(seed), strict=True)
+    if mode == "point":
+        net = nn.DataParallel(ProfileForward2DModel(output_ch=3, params_ch=P, object_ch=200))
+        net.load_state_dict(syn.dynamics2d_state_dict(seed), strict=True)
+    else:
+        net = nn.DataParallel(ProfileForward3DModel(output_ch=3, params_ch=P))
+        net.load_state_dict(syn.dynamics3d_state_dict(seed), strict=True)
+    for p in net.parameters():
+        p.requires_grad = False
+    dm = Diffusion(noise_pred_net=unet, noise_scheduler=_StubDDIM(num_train_timesteps=15), num_inference_steps=5,
+                   mode=mode, input_dim=1, num_points=P, class_cond=True, classifier_model=net, grid_size=grid,
+                   num_pos=npos, object_vertices=objs, object_ids=list(range(len(objs))), sub_batch_size=sub_bs,
+                   seed=seed)
+    dm.eval()
+    return dm
+
+
+def main_big_g():
+    """cond_fn of the real reference at the BASELINE pose grids (2D: 36 x 5 x 5 = 900 rows per candidate, 3D: 45 x 5 x 5 =
+    1125, stock sub-batch 512), a few candidates: the fixtures the unscaled 1e-3 / 2e-2 bounds are checked against."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    install_stubs()
+    import warnings
+    warnings.filterwarnings("ignore")
+    from dynamics.models import pointnet2_utils
+    from dgdm_b200 import synthetic as syn
+    out = {}
+    B2 = 16
+    objs2 = syn.objects_2d(2)
+    dm = _build("point", 36, 5, objs2)
+    n2 = syn.initial_noise(B2, 14, seed=3)
+    out["noise_2d"], out["objects_2d"] = n2.numpy(), objs2.numpy()
+    for t, name in ((6, "rotate_clockwise"), (12, "rotate"), (0, "counterclockwise_left")):
+        g = dm.cond_fn(n2, t * torch.ones((B2,), dtype=torch.int64), opt_obj=name, object_vertices=objs2[1],
+                       ori_range=[-1.0, 1.0])
+        out[f"grad_2d_t{t}_{name}"] = g.detach().numpy()
+    B3 = 8
+    objs3, starts = syn.objects_3d(2), syn.fps_starts(2)
+    dm3 = _build("point_3d", 45, 5, objs3, sub_bs=512)
+    n3 = syn.initial_noise(B3, 42, seed=4)
+    out["noise_3d"], out["objects_3d"], out["fps_starts"] = n3.numpy(), objs3.numpy(), starts.numpy()
+    calls = {"n": 0}
+    real_torch = pointnet2_utils.torch
+
+    def pinned(lo, hi, shape, dtype=torch.long):
+        lvl = calls["n"] % 2
+        calls["n"] += 1
+        return torch.full(shape, int(starts[1, lvl]), dtype=dtype)
+
+    class _TorchProxy:
+        def __getattr__(self, k):
+            return pinned if k == "randint" else getattr(real_torch, k)
+
+    pointnet2_utils.torch = _TorchProxy()
+    for t, name in ((6, "rotate_clockwise"), (3, "rotate")):
+        calls["n"] = 0
+        g = dm3.cond_fn(n3, t * torch.ones((B3,), dtype=torch.int64), opt_obj=name, object_vertices=objs3[1],
+                        ori_range=[-1.0, 1.0])
+        out[f"grad_3d_t{t}_{name}"] = g.detach().numpy()
+    pointnet2_utils.torch = real_torch
+    np.savez_compressed(os.path.join(HERE, "golden_bigG.npz"), **out)
+    print("golden_bigG.npz:", len(out), "arrays")
+
+
+OBJECTIVES_15 = ["rotate", "rotate_clockwise", "rotate_counterclockwise", "shift_up", "shift_down", "shift_left",
+                 "shift_right", "clockwise_up", "clockwise_down", "clockwise_left", "clockwise_right",
+                 "counterclockwise_up", "counterclockwise_down", "counterclockwise_left", "counterclockwise_right"]
+
+
+def main_metrics():
+    """The reference's own metric tables on a seeded set of simulator-style metric dicts (dynamics/metrics.py:67-233
+    metric2objective; generator/diffusion.py:354-428 get_average_best_ids / get_best_ids_all_metrics / get_best_ids),
+    for all 15 non-convergence objectives.  Candidates 2 and 5 are exact copies of candidates 0 and 1, so every
+    arg-min / arg-max has a tie and the first-occurrence rule is pinned too."""
+    install_stubs()
+    from generator.diffusion import Diffusion
+    from dynamics.metrics import metric2objective
+    rs = np.random.RandomState(42)
+    n_cand, n_rot = 7, 36
+    metrics = []
+    for c in range(n_cand):
+        m = {"profile": rs.randint(0, 3, n_rot), "profile_x": rs.randint(0, 3, n_rot), "profile_y": rs.randint(0, 3, n_rot),
+             "delta_theta": rs.randn(n_rot) * 3.0, "delta_pos": rs.randn(n_rot, 2) * 0.004,
+             "final_delta_theta": rs.randn(n_rot) * 20.0, "final_pos": rs.randn(n_rot, 2) * 0.02}
+        metrics.append(m)
+    for dst, src in ((2, 0), (5, 1)):
+        metrics[dst] = {k: v.copy() for k, v in metrics[src].items()}
+    py = lambda v: v.item() if hasattr(v, "item") else v
+    out = {"metrics": [{k: v.tolist() for k, v in m.items()} for m in metrics], "objectives": {}}
+    for name in OBJECTIVES_15:
+        objs = [metric2objective(m, name) for m in metrics]
+        best_all = Diffusion.get_best_ids_all_metrics(None, objs, opt_obj=name)
+        best_avg = Diffusion.get_average_best_ids(None, objs, opt_obj=name)
+        out["objectives"][name] = {"per_candidate": [{k: py(v) for k, v in o.items()} for o in objs],
+                                   "dtypes": {k: type(v).__name__ for k, v in objs[0].items()},
+                                   "best_ids_all_metrics": {k: int(v) for k, v in best_all.items()},
+                                   "average_best_id": int(best_avg)}
+
+    # get_best_ids: per-object blocks of num_grippers candidates, ids offset by the block start
+    class _Self:
+        get_best_ids_all_metrics = lambda self, objs, opt_obj="rotate": Diffusion.get_best_ids_all_metrics(None, objs, opt_obj)
+    objs = [metric2objective(m, "rotate_clockwise") for m in metrics[:6]]
+    blocks = Diffusion.get_best_ids(_Self(), objs, 3, 2, opt_obj="rotate_clockwise")
+    out["get_best_ids_rotate_clockwise_3x2"] = [{k: int(v) for k, v in b.items()} for b in blocks]
+    with open(os.path.join(HERE, "golden_metrics.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("golden_metrics.json:", len(out["objectives"]), "objectives x", n_cand, "candidates")
+
+
 if __name__ == "__main__":
-    main()
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    {"all": main, "bigG": main_big_g, "metrics": main_metrics}[what]()

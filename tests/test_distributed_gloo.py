@@ -48,9 +48,20 @@ def _worker(rank, world, port, n_obj, B, P, k, q):
         m = D.gather_multi_object_results({"scores": sc[lo:hi], "designs": designs[0, lo:hi]}, B, k, sel)
         ok = ok and torch.equal(m["scores"], sc) and torch.equal(m["designs"], designs[0]) \
             and m["best_ids"].tolist() == np.argsort(-sc.numpy(), kind="stable")[:k].tolist()
+        # per-object mode with fewer objects than ranks: candidates sharded, every rank holds all objects
+        c = D.gather_per_object_candidate_shards({"scores": scores[:, lo:hi].contiguous(), "designs": designs[:, lo:hi].contiguous()},
+                                                 B, k, sel)
+        ok = ok and torch.equal(c["scores"], scores) and torch.equal(c["designs"], designs) \
+            and c["best_ids"].numpy().tolist() == order.tolist()
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
+
+
+def test_plan_per_object():
+    assert D.plan_per_object(1024, 8) == "objects" and D.plan_per_object(8, 8) == "objects"
+    assert D.plan_per_object(5, 8) == "candidates" and D.plan_per_object(1, 2) == "candidates"
+    assert D.plan_per_object(5, 1) == "objects"
 
 
 @pytest.mark.parametrize("world,n_obj", [(2, 6), (3, 7), (2, 1)])
