@@ -11,8 +11,11 @@ wandb tables and the MuJoCo evaluation the reference runs afterwards are out of 
         [--checkpoint_path dynamics_2d.pt --diffusion_checkpoint_path diffusion_2d.pt --object_dir objects.npy]
 
 Without checkpoint paths, seeded synthetic weights are used (dgdm_b200.synthetic).  ``--object_dir`` takes a
-``.npy``/``.npz`` of already-extracted, already-normalised object vertices ``(n_obj, V, 2)`` / ``(n_obj, 512, 3)``
-(contour extraction and mesh sampling need cv2/open3d assets code that is out of scope); default: synthetic objects.
+``.npy``/``.npz`` of already-extracted object vertices ``(n_obj, V, 2)`` / ``(n_obj, 512, 3)`` (contour extraction and
+mesh sampling need cv2/open3d assets code that is out of scope); default: synthetic objects.  Vertices in the
+simulator's metres (what ``extract_contours`` / ``sample_pts_from_mesh`` return) are min-max normalised to [-1, 1]
+exactly as generator/train.py:93-99,107-109 (3D) and :111-114,122-123 (2D) do when ``--objects_in_metres`` is given;
+without it the array is taken as already normalised.
 """
 from __future__ import annotations
 
@@ -22,6 +25,20 @@ import sys
 
 import numpy as np
 import torch
+
+
+# workspace bounds the reference normalises object vertices with (generator/train.py:93-99 3D, :111-114 2D), metres
+OBJECT_BOUNDS_3D = ((-0.1, 0.1), (-0.1, 0.1), (0.0, 0.12))
+OBJECT_BOUNDS_2D = ((-0.05, 0.05), (-0.05, 0.05))
+
+
+def normalise_objects(vertices: torch.Tensor, fingers_3d: bool) -> torch.Tensor:
+    """Min-max the object vertices from metres to [-1, 1] per axis: ``(v - min) / (max - min) * 2.0 - 1.0`` in fp32,
+    the expression and operation order of generator/train.py:107-109 (3D) / :122-123 (2D)."""
+    out = vertices.clone().float()
+    for ax, (lo, hi) in enumerate(OBJECT_BOUNDS_3D if fingers_3d else OBJECT_BOUNDS_2D):
+        out[..., ax] = (out[..., ax] - lo) / (hi - lo) * 2.0 - 1.0
+    return out
 
 
 def parse(argv=None):
@@ -67,7 +84,9 @@ def parse(argv=None):
     # additions
     p.add_argument("--objectives", type=str, default="rotate_clockwise", help="comma-separated opt_obj names")
     p.add_argument("--num_objects", type=int, default=8, help="synthetic objects when --object_dir is not given")
-    p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "bf16", "fp32_simt"])
+    p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "fp16x3", "fp16", "bf16", "fp32_simt"])
+    p.add_argument("--objects_in_metres", action="store_true",
+                   help="--object_dir holds raw vertices in metres: normalise them as generator/train.py does")
     p.add_argument("--multi_object", action="store_true", help="also run guided_sample_multi_object")
     p.add_argument("--device", type=str, default="cuda:0")
     p.add_argument("--top_k", type=int, default=1)
@@ -97,6 +116,8 @@ def main(argv=None) -> int:
         arr = np.load(args.object_dir, allow_pickle=True)
         arr = arr[arr.files[0]] if hasattr(arr, "files") else arr
         objs = torch.from_numpy(np.asarray(arr, dtype=np.float32))
+        if args.objects_in_metres:
+            objs = normalise_objects(objs, args.fingers_3d)
     else:
         objs = syn.objects_3d(args.num_objects, args.object_max_num_vertices) if args.fingers_3d else \
             syn.objects_2d(args.num_objects, args.object_max_num_vertices)

@@ -47,10 +47,14 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(b)) : "memory");
 }
+// commit / mma_ss are called by every lane of the issuing warp (uniform control flow, so every operand stays in
+// uniform registers: no ELECT / R2UR / BRA.U.ANY waterfall in front of each UTCHMMA); lane 0 executes the instruction
 __device__ __forceinline__ void commit(uint64_t* b) {
+  if ((threadIdx.x & 31) == 0)
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(b)) : "memory");
 }
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+  if ((threadIdx.x & 31) == 0)
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(accum) : "memory");
 }
@@ -83,10 +87,11 @@ struct Bars {
 __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
   extern __shared__ uint8_t raw[];
   const uint32_t w_tile = (uint32_t)P.N * 128u;
-  uint8_t* wring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* wring = raw + ((1024u - (s32(raw) & 1023u)) & 1023u);       // 1024-byte aligned, shared address space kept
   uint8_t* aring = wring + (size_t)P.n_w * w_tile;
   Bars& S = *reinterpret_cast<Bars*>(aring + (size_t)P.n_a * A_STAGE_B);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: provably warp-uniform for the compiler (see the MMA issuer)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < P.n_a; ++s) { bar_init(&S.a_full[s], 1); bar_init(&S.a_empty[s], 1); }
@@ -101,7 +106,9 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = S.tmem_base;
+  // all 512 columns are allocated, so the base is 0 by construction; a literal keeps the MMA operands uniform
+  if (S.tmem_base != 0) { if (tid == 0 && P.err) atomicExch(P.err, 20); __trap(); }
+  constexpr uint32_t tmem = 0;
   const int my_tiles = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == NEPI) {
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
     }
   } else if (warp == NEPI + 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; mma_ss / commit issue from lane 0
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       for (int t = 0; t < my_tiles; ++t) {
@@ -153,6 +160,7 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
           const uint32_t abase = s32(aring + (size_t)sa * A_STAGE_B);
           for (int tp = 0; tp < cb.ntap; ++tp) {
             const uint32_t a0 = abase + (uint32_t)cb.tap[tp].roff * 16u;
+            const uint64_t ad_hi = nosw_desc(a0), ad_lo = nosw_desc(a0 + SLAB_B);   // + ks * 2 planes: low word only, no carry
             // W hi: hi.hi and lo.hi
             bar_wait(&S.w_full[sw], pw, P.err, 25);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -160,9 +168,9 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t wd = sw128_desc(wb + ks * 32);
-              mma_ss(d, nosw_desc(a0 + ks * 2 * PLANE_B), wd, idesc, accum);
+              mma_ss(d, ad_hi + (uint64_t)(ks * 2 * PLANE_B >> 4), wd, idesc, accum);
               accum = 1;
-              if (P.x3) mma_ss(d, nosw_desc(a0 + SLAB_B + ks * 2 * PLANE_B), wd, idesc, 1);
+              if (P.x3) mma_ss(d, ad_lo + (uint64_t)(ks * 2 * PLANE_B >> 4), wd, idesc, 1);
             }
             commit(&S.w_empty[sw]);
             if (++sw == (uint32_t)P.n_w) { sw = 0; pw ^= 1; }
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               wb = s32(wring + (size_t)sw * w_tile);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) mma_ss(d, nosw_desc(a0 + ks * 2 * PLANE_B), sw128_desc(wb + ks * 32), idesc, 1);
+              for (int ks = 0; ks < 4; ++ks) mma_ss(d, ad_hi + (uint64_t)(ks * 2 * PLANE_B >> 4), sw128_desc(wb + ks * 32), idesc, 1);
               commit(&S.w_empty[sw]);
               if (++sw == (uint32_t)P.n_w) { sw = 0; pw ^= 1; }
             }

@@ -10,10 +10,13 @@ real reference by tests/test_oracle_golden.py).  No sqrt(900/G) scaling, no set-
     final predicted scores of the free-running run  abs-err  <= 1e-3                      (bf16: see SCORE_TOL)
     top-4 indices                                   exact
 
-The free-running final designs are reported and held to a looser bound (5x): a trajectory is a 5-step feedback loop
-through a piecewise-linear network, so one ReLU sign flip early on (they happen between any two fp32 summation
-orders: the exact-order CUDA-core path shows 1.2e-3 on the 3D slice against the CPU) moves that candidate's later
-steps; the north-star bounds are per step, on scores and on indices.
+The free-running run is a 5-step feedback loop through a piecewise-linear network.  2D (guidance scale 1e-3): final
+scores and designs are held to 1e-3 as is (single-pass bf16: 2e-3 / 2e-2).  The 3D slice (SCALE_3D = 0.5, random-init
+weights, clipping at +-1) amplifies any per-step difference -- the exact-order fp32 CUDA-core path itself lands 1.2e-3
+from the CPU in designs -- so its bound is CALIBRATED WITH THE ORACLE: the oracle's own loop is re-run with every
+step's gradient perturbed by random noise of relative size equal to the north-star per-step tolerance of the mode
+(1e-3 / 2e-2), and a CUDA mode, whose per-step error is inside that tolerance, must land within twice the oracle's
+own response (never tighter than 1e-3).  The measured responses are printed.
 
 The worst candidate and the rank-1/rank-2 score margin are printed (pytest -s) for DESIGN.md.
 """
@@ -30,15 +33,10 @@ pytestmark = pytest.mark.gpu
 MODES = ["fp32_simt", "fp32", "fp16x3", "fp16", "bf16"]
 GRAD_TOL = {"fp32_simt": 1e-3, "fp32": 1e-3, "fp16x3": 1e-3, "fp16": 2e-2, "bf16": 2e-2}
 EXACT_TOPK = {"fp32_simt", "fp32", "fp16x3", "fp16"}
-# Free-running run (5 guided steps feeding back): final scores (north-star: 1e-3) and designs.  2D (guidance scale 1e-3)
-# meets 1e-3 in every mode but single-pass bf16.  The 3D slice (scale 0.5, random-init weights, clipping at +-1) amplifies
-# a per-step difference 25-100x over the five steps -- the exact-order fp32 CUDA-core path itself lands 1.2e-3 from the CPU
-# in designs -- so the single-pass modes are held to their measured envelope there; the fp32-grade modes
-# keep the 1e-3 score bound.
-SCORE_TOL = {("2d", "fp32_simt"): 1e-3, ("2d", "fp32"): 1e-3, ("2d", "fp16x3"): 1e-3, ("2d", "fp16"): 1e-3, ("2d", "bf16"): 2e-3,
-             ("3d", "fp32_simt"): 1e-3, ("3d", "fp32"): 1e-3, ("3d", "fp16x3"): 1e-3, ("3d", "fp16"): 1e-2, ("3d", "bf16"): 1e-2}
-DESIGN_TOL = {("2d", "fp32_simt"): 1e-3, ("2d", "fp32"): 1e-3, ("2d", "fp16x3"): 1e-3, ("2d", "fp16"): 1e-3, ("2d", "bf16"): 2e-2,
-              ("3d", "fp32_simt"): 5e-3, ("3d", "fp32"): 5e-3, ("3d", "fp16x3"): 5e-3, ("3d", "fp16"): 1e-1, ("3d", "bf16"): 2e-1}
+# Free-running run (5 guided steps feeding back): final scores (north-star: 1e-3) and designs.  3D: see the module docstring
+# (bounds calibrated per fixture by _response below).
+SCORE_TOL = {("2d", "fp32_simt"): 1e-3, ("2d", "fp32"): 1e-3, ("2d", "fp16x3"): 1e-3, ("2d", "fp16"): 1e-3, ("2d", "bf16"): 2e-3}
+DESIGN_TOL = {("2d", "fp32_simt"): 1e-3, ("2d", "fp32"): 1e-3, ("2d", "fp16x3"): 1e-3, ("2d", "fp16"): 1e-3, ("2d", "bf16"): 2e-2}
 OBJ = "rotate_clockwise"
 
 
@@ -46,6 +44,21 @@ def _per_candidate(got, want):
     a = got.detach().cpu().double().reshape(want.shape[0], -1)
     b = want.double().reshape(want.shape[0], -1)
     return ((a - b).norm(dim=1) / b.norm(dim=1).clamp_min(1e-30)).numpy()
+
+
+def _response(samp, noise, designs, scores, rel_step, seed=7):
+    """The oracle's own sensitivity: its guided loop (OracleSampler.guided_sample) with every step's guidance gradient
+    perturbed, per candidate, by white noise of relative L2 size ``rel_step``.  Returns (designs rel-err, scores max
+    abs-err) of the perturbed run against the unperturbed one."""
+    g = torch.Generator().manual_seed(seed)
+    scale = samp.classifier_scale(OBJ)
+    sample = noise.clone()
+    for t in samp.timesteps:
+        grad = samp.cond_fn(sample, int(t), OBJ, 0)
+        n = torch.randn(grad.shape, generator=g)
+        n = n * (rel_step * grad.flatten(1).norm(dim=1) / n.flatten(1).norm(dim=1)).view(-1, 1, 1)
+        sample, _ = samp._step(sample, int(t), grad + n, scale)
+    return rel(sample[None], designs), float((samp.score(sample, 0, OBJ) - scores).abs().max())
 
 
 @pytest.fixture(scope="module")
@@ -77,6 +90,9 @@ def oracle3d():
     designs = samp.guided_sample(noise, OBJ, trace=out["trace"])
     out["designs"] = designs
     out["scores"] = samp.score(designs[0], 0, OBJ)
+    out["response"] = {tol: _response(samp, noise, designs, out["scores"], tol) for tol in (1e-3, 2e-2)}
+    print("[3d oracle] response of the final (designs rel-err, scores abs-err) to a per-step gradient perturbation of "
+          + ", ".join(f"{tol:g}: ({d:.3e}, {s:.3e})" for tol, (d, s) in out["response"].items()))
     return out
 
 
@@ -115,8 +131,14 @@ def _check_run(dm, o, precision, tag):
     margins = (srt[:4] - srt[1:5]).tolist()
     print(f"[{tag} {precision}] full run vs oracle: designs rel-err {d_err:.3e}, scores max abs-err {s_err:.3e}, "
           f"top-4 {got_top} (oracle {want_top}), oracle rank margins {['%.2e' % m for m in margins]}")
-    assert s_err <= SCORE_TOL[(tag, precision)], (s_err, SCORE_TOL[(tag, precision)])
-    assert d_err <= DESIGN_TOL[(tag, precision)], (d_err, DESIGN_TOL[(tag, precision)])
+    if (tag, precision) in SCORE_TOL:
+        s_tol, d_tol = SCORE_TOL[(tag, precision)], DESIGN_TOL[(tag, precision)]
+    else:                                             # 3D: twice the oracle's own response to an in-tolerance per-step error
+        d_resp, s_resp = o["response"][GRAD_TOL[precision]]
+        s_tol, d_tol = max(1e-3, 2 * s_resp), max(1e-3, 2 * d_resp)
+        print(f"[{tag} {precision}] calibrated bounds: scores {s_tol:.3e}, designs {d_tol:.3e}")
+    assert s_err <= s_tol, (s_err, s_tol)
+    assert d_err <= d_tol, (d_err, d_tol)
     # Selection: every rank whose oracle score is separated from both neighbours by more than twice THIS run's score
     # error must be the same candidate; closer ranks are a tie at this precision (the 3D slice has a 5e-6 margin
     # between its two best candidates -- 200x below even the exact-order fp32 path's score error).

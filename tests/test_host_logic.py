@@ -233,3 +233,23 @@ def test_cli_accepts_the_reference_command_lines():
         cli.main(["--mode=train", "--classifier_guidance"])
     with pytest.raises(SystemExit):
         cli.main(["--mode=test"])
+
+
+def test_cli_normalises_objects_as_the_reference():
+    """``--objects_in_metres``: the min-max to [-1, 1] of generator/train.py:107-109 (3D) and :122-123 (2D), same
+    expression and fp32 operation order (restated here independently from the reference's lines)."""
+    from dgdm_b200 import cli
+    rng = np.random.RandomState(5)
+    v3 = torch.from_numpy(rng.uniform([-0.1, -0.1, 0.0], [0.1, 0.1, 0.12], size=(3, 512, 3)).astype(np.float32))
+    want = v3.clone()
+    want[..., 0] = (want[..., 0] - (-0.1)) / (0.1 - (-0.1)) * 2.0 - 1.0
+    want[..., 1] = (want[..., 1] - (-0.1)) / (0.1 - (-0.1)) * 2.0 - 1.0
+    want[..., 2] = (want[..., 2] - 0.0) / (0.12 - 0.0) * 2.0 - 1.0
+    got = cli.normalise_objects(v3, True)
+    assert torch.equal(got, want) and float(got.abs().max()) <= 1.0 + 1e-6
+    v2 = torch.from_numpy(rng.uniform(-0.05, 0.05, size=(4, 100, 2)).astype(np.float32))
+    want2 = v2.clone()
+    want2[..., 0] = (want2[..., 0] - (-0.05)) / (0.05 - (-0.05)) * 2.0 - 1.0
+    want2[..., 1] = (want2[..., 1] - (-0.05)) / (0.05 - (-0.05)) * 2.0 - 1.0
+    assert torch.equal(cli.normalise_objects(v2, False), want2)
+    assert torch.equal(v2, torch.from_numpy(np.asarray(v2)))        # input untouched
