@@ -61,6 +61,13 @@ constexpr int NSTAGE = 5;
 constexpr int NEPI = 16;                       // epilogue warps: 4 per TMEM lane quadrant, 16 features of every k-block each
 constexpr int NTHREADS = (NEPI + 2) * 32;      // + producer warp + MMA warp
 constexpr int MAX_SEG = 20;
+// two-tile single-pass kernel (tc_trunk2_kernel)
+constexpr int NA2 = 5;                         // A-operand ring: k-block slots of 128 rows x 128 B
+constexpr int NW2 = 4;                         // weight ring stages
+constexpr int AKB_BYTES = 128 * 128;           // one A k-block: 16 KB
+constexpr int MAX_ITEMS = 44;                  // work items per tile pair and role: bit 7 = tile slot, bits 0..6 = segment
+constexpr int IT_A1 = 0x7E;                    // item codes 0x7E / 0x7F: build the layer-1 operand, K-half 0 / 1
+constexpr int MAX_CTAS2 = 160;                 // mask scratch is sized for this many CTAs
 constexpr int MASK_WORDS = 16 + 7 * 8;         // layer 1 up to 512 wide + 7 layers of 256
 
 // K_OUT: the 3-wide output layer as a 16-column MMA segment (bf16 mode).  K_FOUT (fp32-grade mode): the last hidden
@@ -90,6 +97,10 @@ struct TcParams {
   float gscale;         // scale of the backward seed (1, or F16_GS in the fp16 modes)
   int alt;              // 1: an odd number of region swaps per tile -> alternate the start region tile by tile
   Seg seg[MAX_SEG];
+  // two-tile kernel (tc_trunk2_kernel): ReLU sign bits live in global scratch, work order lists for the two roles
+  uint16_t* mask_scratch;
+  int n_e, n_m;
+  uint8_t e_items[MAX_ITEMS], m_items[MAX_ITEMS];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -142,6 +153,15 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  if ((threadIdx.x & 31) == 0)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -830,6 +850,433 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
   }
 }
 
+// =============================================================================================
+// tc_trunk2_kernel: the single-pass modes (bf16 / fp16) with TWO row tiles in flight per CTA.
+//
+// In the kernel above a tile's layers form a serial chain (accumulate -> epilogue -> next layer's MMAs), and with one
+// MMA per product the chain (~1000 cycles + fill) is half of a layer's 2048 cycles of tensor work: 0.70 of roofline.
+// A second, independent tile hides it, but does not fit in TMEM next to TS-mode operands (2 x (128 + 256) columns).
+// Here TMEM holds only the two fp32 accumulators (2 x 256 columns); the activations go through shared memory (SS-mode
+// MMAs): the epilogue warps convert one tile's accumulator into 16 KB k-blocks of a small shared-memory RING (canonical
+// K-major SWIZZLE_128B, the same image as a weight tile) while the tensor pipe works on the other tile.  The ReLU sign
+// bits no longer fit in shared memory (2 x 36 KB) and live in a per-CTA global scratch (L2 resident; a thread only ever
+// reads back words it wrote itself).
+//
+//   warp 16   producer: weight tiles of the MMA work list -> NW2-stage ring (cp.async.bulk)
+//   warp 17   MMA issuer: walks the MMA work list (tile slot, segment); per k-block waits for the A ring slot and the
+//             weight stage, issues 4 tcgen05.mma (SS), commits both slots free; commits d_ready[slot] per segment;
+//             waits d_free[slot] before overwriting an accumulator
+//   warps 0-15 epilogue: walk the epilogue work list; per item wait d_ready[slot], tcgen05.ld the accumulator, release it
+//             (d_free) as soon as the last column is in registers, convert, write A k-blocks into the ring
+//             (st.shared + fence.proxy.async + arrive a_full), sign bits to the scratch
+// The two lists (host, tc2_schedule) interleave the tiles so that the ring is FIFO on both sides and no wait is circular.
+// =============================================================================================
+struct Smem2 {
+  uint64_t full[NW2], empty[NW2], a_full[NA2], a_empty[NA2], d_ready[2], d_free[2];
+  uint32_t tmem_base, pad_;
+  alignas(16) float bias[7][256];
+  alignas(16) float w_out[3][256];
+  float b_out[4];
+  float red[4][256];            // per lane-quadrant partial column sums
+  float red_s[4];
+};
+
+#ifdef DGDM_TRUNK_TRACE
+// CTA 0, second tile pair: issuer stamps at item*16 + k, epilogue warp 0 at 2048 + item*16 + k (scripts/dev/trunk2_timeline.py)
+#define TR2(slot_) do { if (blockIdx.x == 0 && t == 1 && lane == 0 && (warp == 0 || warp == NEPI + 1)) g_trace[slot_] = clock64(); } while (0)
+#else
+#define TR2(slot_) do { } while (0)
+#endif
+
+template <bool F16>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* wring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* aring = wring + NW2 * WTILE_BYTES;
+  Smem2& S = *reinterpret_cast<Smem2*>(aring + NA2 * AKB_BYTES);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < NW2; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < NA2; ++s) { mbar_init(&S.a_full[s], NEPI); mbar_init(&S.a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&S.d_ready[s], 1); mbar_init(&S.d_free[s], NEPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 7 * 256; i += NTHREADS) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256] * (F16 ? F16_SA : 1.f);
+  for (int i = tid; i < 3 * 256; i += NTHREADS) S.w_out[i / 256][i % 256] = P.w_out[i];
+  if (tid < 3) S.b_out[tid] = P.b_out[tid];
+  if (warp == NEPI + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (S.tmem_base != 0u) { if (tid == 0 && P.err) atomicExch(P.err, 9); __trap(); }   // literal TMEM addresses below
+
+  const int tiles_mine = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int pairs_mine = (tiles_mine + 1) / 2;
+
+  if (warp == NEPI) {
+    // =============================== producer ===============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < pairs_mine; ++t) {
+        const bool has1 = 2 * t + 1 < tiles_mine;
+        for (int i = 0; i < P.n_m; ++i) {
+          const uint32_t it = P.m_items[i];
+          if ((it >> 7) && !has1) continue;
+          const Seg sgm = P.seg[it & 0x7Fu];
+          const uint32_t tile_bytes = (uint32_t)sgm.n_rows * 128u;
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&S.empty[stage], phase ^ 1, P.err, 1);
+            mbar_arrive_expect_tx(&S.full[stage], tile_bytes);
+            // image order inside a segment: kb0.hi, kb0.lo, kb1.hi, ...; the single-pass modes read the hi parts
+            bulk_g2s(wring + stage * WTILE_BYTES, P.img + sgm.img_off + (size_t)(kb * 2) * tile_bytes, tile_bytes, &S.full[stage]);
+            if (++stage == NW2) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == NEPI + 1) {
+    // =============================== MMA issuer (whole warp, uniform; lane 0 issues) ===============================
+    uint32_t stage = 0, phase = 0, ai = 0, aph = 0, df_ph = 0;
+    for (int t = 0; t < pairs_mine; ++t) {
+      const bool has1 = 2 * t + 1 < tiles_mine;
+      for (int i = 0; i < P.n_m; ++i) {
+        const uint32_t it = P.m_items[i];
+        const uint32_t slot = it >> 7, sg = it & 0x7Fu;
+        if (slot && !has1) continue;
+        const Seg sgm = P.seg[sg];
+        // 3D: the two N-halves of the last backward GEMM read the same operand; the first one keeps the ring slots
+        const bool hold = sgm.kind == K_LAST && (int)sg != P.n_seg - 1;
+        TR2(i * 16 + 0);
+        if (!sgm.accum) {                        // this segment overwrites the accumulator: the epilogue must have read it
+          mbar_wait(&S.d_free[slot], ((df_ph >> slot) & 1u) ^ 1u, P.err, 5);
+          df_ph ^= 1u << slot;
+          tc_fence_after();
+        }
+        TR2(i * 16 + 1);
+        const uint32_t d_base = slot * 256u;
+        const uint32_t idesc = make_idesc<F16>(sgm.n_rows);
+        uint32_t accum = sgm.accum, a_i = ai, a_p = aph;
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&S.a_full[a_i], a_p, P.err, 2);
+          TR2(i * 16 + 2 + kb * 3);
+          mbar_wait(&S.full[stage], phase, P.err, 3);
+          tc_fence_after();
+          TR2(i * 16 + 3 + kb * 3);
+          const uint32_t a_addr = smem_u32(aring + a_i * AKB_BYTES), b_addr = smem_u32(wring + stage * WTILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KBLK / 16; ++ks) {
+            tc_mma_ss(d_base, make_b_desc(a_addr + ks * 32), make_b_desc(b_addr + ks * 32), idesc, accum);
+            accum = 1;
+          }
+          tc_commit(&S.empty[stage]);
+          if (!hold) tc_commit(&S.a_empty[a_i]);
+          TR2(i * 16 + 4 + kb * 3);
+          if (++stage == NW2) { stage = 0; phase ^= 1; }
+          if (++a_i == NA2) { a_i = 0; a_p ^= 1; }
+        }
+        if (!hold) { ai = a_i; aph = a_p; }
+        if (sgm.kind != K_MID) tc_commit(&S.d_ready[slot]);
+        TR2(i * 16 + 14);
+      }
+    }
+  } else {
+    // =============================== epilogue warps 0..15 ===============================
+    const int q = warp & 3, hq = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int l1_hw = P.H1 / 16;
+    uint32_t ei = 0, eph = 0, dr_ph = 0;
+    uint16_t* const mask_cta = P.mask_scratch + (size_t)blockIdx.x * 2 * (2 * MASK_WORDS) * TILE_M + row;
+
+    // this warp's 32 rows x 16 features of the next A k-block -> ring slot (canonical K-major SWIZZLE_128B)
+    [[maybe_unused]] int tr_i = 0, tr_t = 0, tr_kb = 0;
+    auto put_kb = [&](const uint32_t (&hi)[8]) {
+      mbar_wait(&S.a_empty[ei], eph ^ 1u, P.err, 6);
+#ifdef DGDM_TRUNK_TRACE
+      { const int t = tr_t; TR2(2048 + tr_i * 16 + 8 + (tr_kb & 3)); }
+#endif
+      uint8_t* dst = aring + ei * AKB_BYTES + row * 128;
+      const int sw = row & 7;
+      *reinterpret_cast<uint4*>(dst + (((2 * hq) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(dst + (((2 * hq + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.a_full[ei]);
+#ifdef DGDM_TRUNK_TRACE
+      { const int t = tr_t; TR2(2048 + tr_i * 16 + 2 + (tr_kb & 3)); ++tr_kb; }
+#endif
+      if (++ei == NA2) { ei = 0; eph ^= 1u; }
+    };
+
+    for (int t = 0; t < pairs_mine; ++t) {
+      const bool has1 = 2 * t + 1 < tiles_mine;
+      for (int i = 0; i < P.n_e; ++i) {
+        const uint32_t it = P.e_items[i];
+        const uint32_t slot = it >> 7;
+        const int code = (int)(it & 0x7Fu);
+        if (slot && !has1) continue;
+        tr_i = i; tr_t = t; tr_kb = 0;
+        TR2(2048 + i * 16 + 0);
+        const int tile = (int)blockIdx.x + (2 * t + (int)slot) * (int)gridDim.x;
+        uint16_t* const mk = mask_cta + (size_t)slot * (2 * MASK_WORDS) * TILE_M;     // word w of this row: mk[w * TILE_M]
+
+        // Row -> (pair, pose row): one 64-bit division per item that needs it, everything per row is 32-bit.
+        const int64_t base = (int64_t)tile * TILE_M;
+        const int64_t r_glob = base + row;
+        const bool live = r_glob < P.n_rows;
+
+        if (code >= IT_A1) {
+          // ---- layer-1 operand, K-half kh: relu(Cst[obj] + U[design] + V[g]) for the 64 features this warp owns ----
+          const int kh = code - IT_A1;
+          const int64_t p_first = base / P.G;
+          const uint32_t rem0 = (uint32_t)(base - p_first * P.G), Gu = (uint32_t)P.G;
+          const uint32_t rofs = rem0 + (uint32_t)row, dq = rofs / Gu;
+          const int64_t pr = live ? p_first + dq : -1;
+          const int g = live ? (int)(rofs - dq * Gu) : 0;
+          const float* u_row = nullptr; const float* c_row = nullptr;
+          if (live) {
+            const int64_t design = P.opd == 1 ? pr : (pr <= 0x7fffffffll ? (int64_t)((uint32_t)pr / (uint32_t)P.opd) : pr / P.opd);
+            u_row = P.U + design * P.H1;
+            c_row = P.Cst + (int64_t)pair_obj(pr, P.opd, P.n_designs, P.n_obj, P.pair_object) * P.H1;
+          }
+          auto load_z = [&](int col0, float (&z)[16]) {
+            float pv[16];
+            const float* vt = P.Vt + (int64_t)col0 * P.G + g;
+            const uint32_t G32 = (uint32_t)P.G;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pv[k] = live ? __ldg(vt + k * G32) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (live) {
+                const float4 k4 = *reinterpret_cast<const float4*>(c_row + col0 + k);
+                const float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + k);
+                a.x = (k4.x + u4.x) + pv[k]; a.y = (k4.y + u4.y) + pv[k + 1]; a.z = (k4.z + u4.z) + pv[k + 2]; a.w = (k4.w + u4.w) + pv[k + 3];
+              }
+              if (F16) { a.x *= F16_SA; a.y *= F16_SA; a.z *= F16_SA; a.w *= F16_SA; }
+              z[k] = a.x; z[k + 1] = a.y; z[k + 2] = a.z; z[k + 3] = a.w;
+            }
+          };
+          float zb[2][16];
+          load_z(kh * 256 + hq * 16, zb[0]);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            if (kb + 1 < 4) load_z(kh * 256 + (kb + 1) * 64 + hq * 16, zb[(kb + 1) & 1]);
+            uint32_t hi[8], lo[8];
+            relu_split16<false, F16>(zb[kb & 1], hi, lo);
+            put_kb(hi);
+            __stcg(mk + (kh * 16 + kb * 4 + hq) * TILE_M, (uint16_t)sign_bits16(hi));
+          }
+          TR2(2048 + i * 16 + 6);
+          continue;
+        }
+
+        const Seg sgm = P.seg[code];
+        const uint32_t d_addr = lane_addr + slot * 256u;
+        // the accumulator may be overwritten once every epilogue warp has its columns in registers
+        auto release_d = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.d_free[slot]);
+        };
+        auto wait_d = [&]() {
+          mbar_wait(&S.d_ready[slot], (dr_ph >> slot) & 1u, P.err, 4);
+          dr_ph ^= 1u << slot;
+          tc_fence_after();
+        };
+
+        if (sgm.kind == K_FWD) {
+          // a = relu(D + b) -> next A operand; sign bits of this layer
+          const int mbase = l1_hw + (sgm.layer - 1) * 16;
+          wait_d();
+          TR2(2048 + i * 16 + 1);
+          uint32_t rr[2][16];
+          tmem_ld16_async(d_addr + (uint32_t)(hq * 16), rr[0]);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            tmem_ld_wait16(rr[kb & 1]);
+            if (kb + 1 < 4) tmem_ld16_async(d_addr + (uint32_t)((kb + 1) * 64 + hq * 16), rr[(kb + 1) & 1]);
+            else release_d();
+            const float4* b4 = reinterpret_cast<const float4*>(&S.bias[sgm.layer - 1][kb * 64 + hq * 16]);
+            float z[16];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 bb = b4[i4];
+              z[i4 * 4 + 0] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 0], bb.x);
+              z[i4 * 4 + 1] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 1], bb.y);
+              z[i4 * 4 + 2] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 2], bb.z);
+              z[i4 * 4 + 3] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 3], bb.w);
+            }
+            uint32_t hi[8], lo[8];
+            relu_split16<false, F16>(z, hi, lo);
+            put_kb(hi);
+            __stcg(mk + (mbase + kb * 4 + hq) * TILE_M, (uint16_t)sign_bits16(hi));
+          }
+          TR2(2048 + i * 16 + 6);
+        } else if (sgm.kind == K_BWD) {
+          // d = D * 1[a_layer > 0] -> next A operand
+          const int mbase = sgm.layer == 0 ? 0 : l1_hw + (sgm.layer - 1) * 16;
+          uint32_t bits[4];
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) bits[kb] = __ldcg(mk + (mbase + kb * 4 + hq) * TILE_M);   // in flight during the wait
+          wait_d();
+          TR2(2048 + i * 16 + 1);
+          uint32_t rr[2][16];
+          tmem_ld16_async(d_addr + (uint32_t)(hq * 16), rr[0]);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            tmem_ld_wait16(rr[kb & 1]);
+            if (kb + 1 < 4) tmem_ld16_async(d_addr + (uint32_t)((kb + 1) * 64 + hq * 16), rr[(kb + 1) & 1]);
+            else release_d();
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = (bits[kb] >> mask_pos(k)) & 1u ? unscale<F16>(rr[kb & 1][k]) : 0.f;
+            uint32_t hi[8], lo[8];
+            split_pack<false, F16>(v, hi, lo);
+            put_kb(hi);
+          }
+          TR2(2048 + i * 16 + 6);
+        } else {
+          // K_OUT and K_LAST need the row's pair
+          const int64_t p_first = base / P.G;
+          const uint32_t rem0 = (uint32_t)(base - p_first * P.G), Gu = (uint32_t)P.G;
+          const uint32_t rofs = rem0 + (uint32_t)row, dq = rofs / Gu;
+          const int64_t pr = live ? p_first + dq : -1;
+          int64_t last_row = base + TILE_M - 1;
+          if (last_row >= P.n_rows) last_row = P.n_rows - 1;
+          const int64_t p_last = p_first + (rem0 + (uint32_t)(last_row - base)) / Gu;
+          if (sgm.kind == K_OUT) {
+            const float coef = (live && P.obj.row_coef) ? P.obj.row_coef[r_glob] : 1.f;
+            const int mbase = l1_hw + 6 * 16;
+            uint32_t bits[4] = {0u, 0u, 0u, 0u};
+            if (P.backward) {
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) bits[kb] = __ldcg(mk + (mbase + kb * 4 + hq) * TILE_M);
+            }
+            wait_d();
+            TR2(2048 + i * 16 + 1);
+            uint32_t rr[8];
+            tmem_ld8(d_addr, rr);
+            release_d();
+            constexpr float inv_out = F16 ? 1.f / (F16_SA * F16_SW) : 1.f;
+            const float l0 = __uint_as_float(rr[0]) * inv_out + S.b_out[0], l1 = __uint_as_float(rr[1]) * inv_out + S.b_out[1],
+                        l2 = __uint_as_float(rr[2]) * inv_out + S.b_out[2];
+            if (hq == 0 && live && P.logits) {
+              float* o = P.logits + r_glob * 3;
+              o[0] = l0; o[1] = l1; o[2] = l2;
+            }
+            if (!P.backward) {
+              const float val = live ? coef * (P.obj.c[0] * l0 + P.obj.c[1] * l1 + P.obj.c[2] * l2 + P.obj.sq0 * l0 * l0) : 0.f;
+              if (P.G == 1) {
+                if (hq == 0 && live) P.score_part[pr + tile] = val;
+              } else
+              for (int64_t ps = p_first; ps <= p_last; ++ps) {
+                float s = (pr == ps) ? val : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (hq == 0 && lane == 0) S.red_s[q] = s;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (tid == 0) P.score_part[ps + tile] = (S.red_s[0] + S.red_s[1]) + (S.red_s[2] + S.red_s[3]);
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+              }
+            } else {
+              // seed of the backward pass: d8 = (dObj/dlogits . W_out) * 1[a_8 > 0]
+              const float cg = coef * P.gscale;
+              const float dl0 = cg * (P.obj.c[0] + 2.f * P.obj.sq0 * l0), dl1 = cg * P.obj.c[1], dl2 = cg * P.obj.c[2];
+#pragma unroll 1
+              for (int kb = 0; kb < 4; ++kb) {
+                const int col0 = kb * 64 + hq * 16;
+                float v[16];
+                const float4* w0 = reinterpret_cast<const float4*>(&S.w_out[0][col0]);
+                const float4* w1 = reinterpret_cast<const float4*>(&S.w_out[1][col0]);
+                const float4* w2 = reinterpret_cast<const float4*>(&S.w_out[2][col0]);
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const float4 a0 = w0[i4], a1 = w1[i4], a2 = w2[i4];
+                  const float d[4] = {dl0 * a0.x + dl1 * a1.x + dl2 * a2.x, dl0 * a0.y + dl1 * a1.y + dl2 * a2.y,
+                                      dl0 * a0.z + dl1 * a1.z + dl2 * a2.z, dl0 * a0.w + dl1 * a1.w + dl2 * a2.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[i4 * 4 + e] = (bits[kb] >> mask_pos(i4 * 4 + e)) & 1u ? d[e] : 0.f;
+                }
+                uint32_t hi[8], lo[8];
+                split_pack<false, F16>(v, hi, lo);
+                put_kb(hi);
+              }
+            }
+            TR2(2048 + i * 16 + 6);
+          } else {
+            // ---- K_LAST: d1 = D * 1[a_1 > 0], summed over the rows of each pair present in the tile (K2) ----
+            // warp (q, hq) reduces the 4 x 16 columns whose layer-1 sign bits it wrote itself: two 32-value chunks
+            uint32_t bits[4];
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) bits[kb] = __ldcg(mk + (sgm.half * 16 + kb * 4 + hq) * TILE_M);
+            wait_d();
+            TR2(2048 + i * 16 + 1);
+            if (P.G == 1) {                           // explicit-row mode: the row IS the pair; store it directly
+#pragma unroll 1
+              for (int kb = 0; kb < 4; ++kb) {
+                uint32_t rr[16];
+                tmem_ld16_async(d_addr + (uint32_t)(kb * 64 + hq * 16), rr);
+                tmem_ld_wait16(rr);
+                if (live) {
+                  float4* o = reinterpret_cast<float4*>(P.part + (pr + tile) * P.H1 + sgm.half * 256 + kb * 64 + hq * 16);
+#pragma unroll
+                  for (int k = 0; k < 16; k += 4) {
+                    float e[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) e[j] = (bits[kb] >> mask_pos(k + j)) & 1u ? __uint_as_float(rr[k + j]) : 0.f;
+                    o[k / 4] = make_float4(e[0], e[1], e[2], e[3]);
+                  }
+                }
+              }
+              release_d();
+            } else
+            for (int64_t ps = p_first; ps <= p_last; ++ps) {
+              const bool mine = pr == ps;
+#pragma unroll 1
+              for (int c = 0; c < 2; ++c) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16_async(d_addr + (uint32_t)((2 * c) * 64 + hq * 16), r0);
+                tmem_ld16_async(d_addr + (uint32_t)((2 * c + 1) * 64 + hq * 16), r1);
+                tmem_ld_wait16(r0);
+                tmem_ld_wait16(r1);
+                if (ps == p_last && c == 1) release_d();
+                const uint32_t b0 = mine ? bits[2 * c] : 0u, b1 = mine ? bits[2 * c + 1] : 0u;
+                float v[32];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  v[k] = (b0 >> mask_pos(k)) & 1u ? __uint_as_float(r0[k]) : 0.f;
+                  v[16 + k] = (b1 >> mask_pos(k)) & 1u ? __uint_as_float(r1[k]) : 0.f;
+                }
+                const float sum = warp_transpose_sum(v, lane);
+                S.red[q][(2 * c + (lane >> 4)) * 64 + hq * 16 + (lane & 15)] = sum;
+              }
+              asm volatile("bar.sync 1, 512;" ::: "memory");
+              if (tid < 256) {
+                const float s = (S.red[0][tid] + S.red[1][tid]) + (S.red[2][tid] + S.red[3][tid]);
+                P.part[(ps + tile) * P.H1 + sgm.half * 256 + tid] = s;
+              }
+              asm volatile("bar.sync 1, 512;" ::: "memory");
+            }
+            TR2(2048 + i * 16 + 6);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NEPI + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(0u) : "memory");
+  }
+}
+
 // K2 tail: dUp[p,:] = sum over the tiles covering pair p of part[p + tile,:], ascending tile order.
 __global__ void reduce_slots_kernel(float* __restrict__ dUp, const float* __restrict__ part, int64_t n_pairs, int G, int H1,
                                     float inv_gscale) {
@@ -918,6 +1365,50 @@ Plan make_plan(const dgdm_dyn_weights* w, int H1) {
 }
 
 size_t smem_bytes() { return 1024 + (size_t)NSTAGE * WTILE_BYTES + sizeof(Smem); }
+size_t smem2_bytes() { return 1024 + (size_t)NW2 * WTILE_BYTES + (size_t)NA2 * AKB_BYTES + sizeof(Smem2); }
+constexpr size_t MASK_SCRATCH_BYTES = (size_t)MAX_CTAS2 * 2 * (2 * MASK_WORDS) * TILE_M * sizeof(uint16_t);
+
+// DGDM_TRUNK2=1 runs the single-pass modes on the two-tile kernel.  Off by default: it is parity-green but not faster
+// (0.71 vs 0.74 of roofline at C2) -- with the activations in shared memory the SS-mode MMAs read A (32 B/clk) and B
+// (64 B/clk) while the weight ring refills at 64 B/clk and the epilogue stores 32 B/clk: 192 B/clk against the
+// 128 B/clk shared memory delivers, so a layer of a tile takes ~3400 cycles there as well (timeline
+// profiles/trunk2_timeline_r02_bf16.txt).
+bool use_trunk2() {
+  static const bool on = [] { const char* e = getenv("DGDM_TRUNK2"); return e && e[0] == '1'; }();
+  return on;
+}
+
+// Work lists of the two-tile kernel for one pair of tiles (slot 0 = X, slot 1 = Y).  The epilogue list is the
+// interleave E(X,sg), E(Y,sg); the MMA list is derived from it so that the issuer consumes the A ring in exactly the
+// order the epilogue fills it: an item that produces an operand (A1, K_FWD, K_BWD, K_OUT when a backward follows)
+// enables the next segment of its tile.  3D backward tail: the two N-halves of the last GEMM share one operand, which
+// stays in the ring until the second half has run -- and the second half waits for the first half's epilogue -- so
+// X's first half is reduced BEFORE Y's operand is produced (with the plain interleave Y's production would wait for
+// ring slots X cannot release: a circular wait with a 5-slot ring).
+void tc2_schedule(TcParams& P) {
+  int ne = 0, nm = 0;
+  auto E = [&](int slot, int code) { P.e_items[ne++] = (uint8_t)((slot << 7) | code); };
+  const bool two_half = P.H1 == 512;
+  const int n = P.n_seg, first = two_half ? 1 : 0;
+  const bool tail3d = two_half && P.backward;
+  for (int slot = 0; slot < 2; ++slot) {
+    E(slot, IT_A1);
+    if (two_half) E(slot, IT_A1 + 1);
+  }
+  for (int sg = first; sg < (tail3d ? n - 3 : n); ++sg) { E(0, sg); E(1, sg); }
+  if (tail3d) { E(0, n - 3); E(0, n - 2); E(1, n - 3); E(0, n - 1); E(1, n - 2); E(1, n - 1); }
+  for (int i = 0; i < ne; ++i) {
+    const int slot = P.e_items[i] >> 7, code = P.e_items[i] & 0x7F;
+    int next = -1;
+    if (code >= IT_A1) next = code - IT_A1;
+    else {
+      const int kind = P.seg[code].kind;
+      if (kind == K_FWD || kind == K_BWD || (kind == K_OUT && P.backward) || (kind == K_LAST && code != n - 1)) next = code + 1;
+    }
+    if (next >= 0) P.m_items[nm++] = (uint8_t)((slot << 7) | next);
+  }
+  P.n_e = ne; P.n_m = nm;
+}
 
 // event-pair timing of the trunk kernel (bench.py roofline)
 // Off by default.  Launches made while the stream is being captured into a CUDA graph are not timed (events cannot
@@ -938,7 +1429,8 @@ Timing g_timing;
 size_t tc_trunk_workspace_bytes(int H1, int64_t n_pairs, int G) {
   int64_t n_tiles = (n_pairs * G + TILE_M - 1) / TILE_M;
   int64_t slots = n_pairs + n_tiles;
-  return align_up((size_t)slots * H1 * sizeof(float), 256) + align_up((size_t)slots * sizeof(float), 256) + 256;
+  return align_up((size_t)slots * H1 * sizeof(float), 256) + align_up((size_t)slots * sizeof(float), 256) + 256 +
+         align_up(MASK_SCRATCH_BYTES, 256);
 }
 
 int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const float* V, int n_designs, int n_obj,
@@ -953,6 +1445,7 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   float* part = ar.take<float>((size_t)(n_pairs + n_tiles) * H1);
   float* score_part = ar.take<float>((size_t)(n_pairs + n_tiles));
   int* err = ar.take<int>(1);
+  uint16_t* mask_scratch = ar.take<uint16_t>(MASK_SCRATCH_BYTES / sizeof(uint16_t));
   if (!ar.ok) { set_error("tc_trunk: workspace too small"); return DGDM_EWORKSPACE; }
 
   // per-device one-time setup (one process normally drives one GPU, but do not assume it)
@@ -967,6 +1460,8 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
     DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2_bytes()));
     sm_counts[dev] = n;
   }
   const int sm_count = sm_counts[dev];
@@ -996,9 +1491,13 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   }
   P.n_seg = n_seg;
   P.alt = (P.x3 && backward) ? 1 : 0;
+  const bool two_tile = !P.x3 && use_trunk2();
+  P.mask_scratch = mask_scratch;
+  if (two_tile) tc2_schedule(P);
 
   DGDM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
-  const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+  int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+  if (two_tile && grid > MAX_CTAS2) grid = MAX_CTAS2;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   std::unique_lock<std::mutex> timing_lock(g_timing.mu);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -1013,7 +1512,9 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
     g_timing.pair_rows.push_back(n_rows);
     DGDM_CUDA(cudaEventRecord(e0, s));
   }
-  if (P.x3 && f16) tc_trunk_kernel<true, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
+  if (two_tile && f16) tc_trunk2_kernel<true><<<grid, NTHREADS, smem2_bytes(), s>>>(P);
+  else if (two_tile) tc_trunk2_kernel<false><<<grid, NTHREADS, smem2_bytes(), s>>>(P);
+  else if (P.x3 && f16) tc_trunk_kernel<true, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else if (P.x3) tc_trunk_kernel<true, false><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else if (f16) tc_trunk_kernel<false, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else tc_trunk_kernel<false, false><<<grid, NTHREADS, smem_bytes(), s>>>(P);

@@ -7,7 +7,11 @@ reference contract: objects are independent, generator/diffusion.py:561-576).
 
 Every rank runs its shard of a 3D object set through ``distributed.sharded_guided_sample`` (objects sharded; with
 ``--objects`` < N, candidates sharded), rank 0 also runs the whole set alone, and the two are compared: object shards
-must match BIT FOR BIT (scores, best ids, designs), candidate shards to 1e-5 with identical selection.
+must match BIT FOR BIT (scores, best ids, designs).  Candidate shards change the 128-row tile alignment of every pair,
+i.e. the fp32 summation order of its pose rows (~1e-6 per step): identical selection is required, scores / designs to
+1e-5 in 2D (guidance scale 1e-3) and to 1e-4 / 5e-3 in 3D, where the five-step loop (SCALE_3D = 0.5, random-init
+weights) amplifies any reassociation through ReLU sign flips (measured 7e-6 / 9e-4; the CPU oracle's own response to a
+2.5e-4 per-step perturbation is 2e-3 / 2.5e-2, tests/test_gpu_baseline_shape.py).
 Prints one JSON line on rank 0; exit code 1 on a mismatch."""
 import argparse
 import json
@@ -64,7 +68,8 @@ def main():
             elif k == "best_ids":
                 ok = ok and eq
             else:
-                ok = ok and err <= 1e-5 * max(1.0, float(want[k].abs().max()))
+                tol = 1e-5 if not is3d else (5e-3 if k == "designs" else 1e-4)
+                ok = ok and err <= tol * max(1.0, float(want[k].abs().max()))
         report["ok"] = ok
         print(json.dumps(report))
     if world > 1:

@@ -44,10 +44,12 @@ def test_object_shards_reproduce_one_rank_bit_for_bit(precision):
     assert all(rep[k]["bit_exact"] for k in ("scores", "designs", "best_ids", "best_scores"))
 
 
-def test_candidate_shards_when_fewer_objects_than_ranks():
+@pytest.mark.parametrize("mode", ["point_3d", "point"])
+def test_candidate_shards_when_fewer_objects_than_ranks(mode):
     w = _world()
     if w < 2:
         pytest.skip("needs >= 2 GPUs")
     # the stock 3D set is 5 objects (assets/object_names_test.txt); with 1 object even 2 ranks shard candidates
-    rep = _run(w, "--objects", "1" if w == 2 else "5", "--candidates", "64", "--precision", "fp32")
+    rep = _run(w, "--objects", "1" if w == 2 else "5", "--candidates", "64", "--precision", "fp32", "--mode", mode,
+               *(["--grid", "36"] if mode == "point" else []))
     assert rep["plan"] == "candidates" and rep["best_ids"]["bit_exact"]
