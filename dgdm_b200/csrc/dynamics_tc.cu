@@ -67,6 +67,7 @@ constexpr int NW2 = 4;                         // weight ring stages
 constexpr int AKB_BYTES = 128 * 128;           // one A k-block: 16 KB
 constexpr int MAX_ITEMS = 44;                  // work items per tile pair and role: bit 7 = tile slot, bits 0..6 = segment
 constexpr int IT_A1 = 0x7E;                    // item codes 0x7E / 0x7F: build the layer-1 operand, K-half 0 / 1
+constexpr int NTHREADS2 = (NEPI + 3) * 32;     // two-tile kernel: + producer warp + one MMA issuer warp per tile slot
 constexpr int MAX_CTAS2 = 160;                 // mask scratch is sized for this many CTAs
 constexpr int MASK_WORDS = 16 + 7 * 8;         // layer 1 up to 512 wide + 7 layers of 256
 
@@ -133,6 +134,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
       __trap();
     }
   }
+}
+// Non-blocking poll (acquire): 1 if the phase with this parity has completed.  try_wait may suspend the thread.
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -872,7 +883,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 // The two lists (host, tc2_schedule) interleave the tiles so that the ring is FIFO on both sides and no wait is circular.
 // =============================================================================================
 struct Smem2 {
-  uint64_t full[NW2], empty[NW2], a_full[NA2], a_empty[NA2], d_ready[2], d_free[2];
+  uint64_t full[NW2], empty[NW2], a_full[NA2], a_empty[NA2], d_ready[2], d_free[2], turn[2];
   uint32_t tmem_base, pad_;
   alignas(16) float bias[7][256];
   alignas(16) float w_out[3][256];
@@ -883,13 +894,13 @@ struct Smem2 {
 
 #ifdef DGDM_TRUNK_TRACE
 // CTA 0, second tile pair: issuer stamps at item*16 + k, epilogue warp 0 at 2048 + item*16 + k (scripts/dev/trunk2_timeline.py)
-#define TR2(slot_) do { if (blockIdx.x == 0 && t == 1 && lane == 0 && (warp == 0 || warp == NEPI + 1)) g_trace[slot_] = clock64(); } while (0)
+#define TR2(slot_) do { if (blockIdx.x == 0 && t == 1 && lane == 0 && (warp == 0 || warp >= NEPI + 1)) g_trace[slot_] = clock64(); } while (0)
 #else
 #define TR2(slot_) do { } while (0)
 #endif
 
 template <bool F16>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_constant__ TcParams P) {
+__global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* wring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* aring = wring + NW2 * WTILE_BYTES;
@@ -899,11 +910,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < NW2; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     for (int s = 0; s < NA2; ++s) { mbar_init(&S.a_full[s], NEPI); mbar_init(&S.a_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&S.d_ready[s], 1); mbar_init(&S.d_free[s], NEPI); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&S.d_ready[s], 1); mbar_init(&S.d_free[s], NEPI); mbar_init(&S.turn[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 7 * 256; i += NTHREADS) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256] * (F16 ? F16_SA : 1.f);
-  for (int i = tid; i < 3 * 256; i += NTHREADS) S.w_out[i / 256][i % 256] = P.w_out[i];
+  for (int i = tid; i < 7 * 256; i += NTHREADS2) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256] * (F16 ? F16_SA : 1.f);
+  for (int i = tid; i < 3 * 256; i += NTHREADS2) S.w_out[i / 256][i % 256] = P.w_out[i];
   if (tid < 3) S.b_out[tid] = P.b_out[tid];
   if (warp == NEPI + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
@@ -938,9 +949,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == NEPI + 1) {
-    // =============================== MMA issuer (whole warp, uniform; lane 0 issues) ===============================
-    uint32_t stage = 0, phase = 0, ai = 0, aph = 0, df_ph = 0;
+  } else if (warp == NEPI + 1 || warp == NEPI + 2) {
+    // =============================== MMA issuers (whole warp, uniform; lane 0 issues) ===============================
+    // One issuer warp per tile slot.  The tensor pipe takes MMAs one at a time from a thread (issuing four into an idle
+    // pipe takes ~480 cycles), so whatever a single issuer does between k-blocks -- barrier waits, fences, commits -- is
+    // lost tensor time; with two issuers the other slot's MMAs fill those gaps.  Both walk the same work list and keep
+    // the same ring counters (the producer fills the weight ring, the epilogue the A ring, in list order), each issues
+    // only its own slot's items.  Inside an item the next k-block's barriers are polled before the current k-block's
+    // MMAs are issued, so the answers arrive while the thread is blocked in the issue.
+    // Parity waits are only sound while a waiter is at most one phase ahead of its barrier, and an issuer that skips the
+    // other slot's items could run further ahead than that.  So the list is handed over item by item: an issuer starts
+    // the waits of its item only after the other one has PASSED the waits of the preceding item (turn[]; signalled before
+    // that item's last four MMAs are issued, so the hand-over itself costs the tensor pipe nothing).
+    const uint32_t my_slot = (uint32_t)(warp - (NEPI + 1));
+    uint32_t stage = 0, phase = 0, ai = 0, aph = 0, df_ph = 0, turn_ph = 0;
+    int prev_slot = -1;                           // slot of the previous valid item of the list walk
+    // slot of the valid item that follows item i of pair t (-1: none)
+    auto next_slot = [&](int t, int i) -> int {
+      for (int tt = t; tt < pairs_mine; ++tt) {
+        const bool h1 = 2 * tt + 1 < tiles_mine;
+        for (int j = (tt == t ? i + 1 : 0); j < P.n_m; ++j) {
+          const int sl = P.m_items[j] >> 7;
+          if (sl && !h1) continue;
+          return sl;
+        }
+      }
+      return -1;
+    };
     for (int t = 0; t < pairs_mine; ++t) {
       const bool has1 = 2 * t + 1 < tiles_mine;
       for (int i = 0; i < P.n_m; ++i) {
@@ -950,33 +985,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
         const Seg sgm = P.seg[sg];
         // 3D: the two N-halves of the last backward GEMM read the same operand; the first one keeps the ring slots
         const bool hold = sgm.kind == K_LAST && (int)sg != P.n_seg - 1;
+        const int before = prev_slot;
+        prev_slot = (int)slot;
+        if (slot != my_slot) {                   // the other issuer's item: advance the ring counters past it
+          stage += 4; if (stage >= NW2) { stage -= NW2; phase ^= 1; }      // (NW2 = 4: same stage, other phase)
+          if (!hold) { ai += 4; if (ai >= NA2) { ai -= NA2; aph ^= 1; } }
+          continue;
+        }
+        if (before >= 0 && before != (int)my_slot) {      // hand-over from the other issuer
+          mbar_wait(&S.turn[my_slot], turn_ph, P.err, 7);
+          turn_ph ^= 1u;
+        }
+        const bool hand_over = next_slot(t, i) == (int)(my_slot ^ 1u);
         TR2(i * 16 + 0);
         if (!sgm.accum) {                        // this segment overwrites the accumulator: the epilogue must have read it
-          mbar_wait(&S.d_free[slot], ((df_ph >> slot) & 1u) ^ 1u, P.err, 5);
-          df_ph ^= 1u << slot;
+          mbar_wait(&S.d_free[slot], (df_ph & 1u) ^ 1u, P.err, 5);
+          df_ph ^= 1u;
           tc_fence_after();
         }
         TR2(i * 16 + 1);
         const uint32_t d_base = slot * 256u;
         const uint32_t idesc = make_idesc<F16>(sgm.n_rows);
-        uint32_t accum = sgm.accum, a_i = ai, a_p = aph;
+        uint32_t accum = sgm.accum, a_i = ai, a_p = aph, hA = 0, hW = 0;
         for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&S.a_full[a_i], a_p, P.err, 2);
+          if (!hA) mbar_wait(&S.a_full[a_i], a_p, P.err, 2);
           TR2(i * 16 + 2 + kb * 3);
-          mbar_wait(&S.full[stage], phase, P.err, 3);
+          if (!hW) mbar_wait(&S.full[stage], phase, P.err, 3);
           tc_fence_after();
           TR2(i * 16 + 3 + kb * 3);
+          if (kb == 3 && hand_over && lane == 0) mbar_arrive(&S.turn[my_slot ^ 1u]);   // all waits of this item are behind us
           const uint32_t a_addr = smem_u32(aring + a_i * AKB_BYTES), b_addr = smem_u32(wring + stage * WTILE_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < KBLK / 16; ++ks) {
-            tc_mma_ss(d_base, make_b_desc(a_addr + ks * 32), make_b_desc(b_addr + ks * 32), idesc, accum);
-            accum = 1;
-          }
-          tc_commit(&S.empty[stage]);
-          if (!hold) tc_commit(&S.a_empty[a_i]);
-          TR2(i * 16 + 4 + kb * 3);
+          const uint32_t st_cur = stage, a_cur = a_i;
           if (++stage == NW2) { stage = 0; phase ^= 1; }
           if (++a_i == NA2) { a_i = 0; a_p ^= 1; }
+          if (kb < 3) {                           // poll the next k-block's barriers now (see above)
+            hA = mbar_test(&S.a_full[a_i], a_p);
+            hW = mbar_test(&S.full[stage], phase);
+          }
+          // descriptors of the four K = 16 steps: + 32 bytes = + 2 in the 14-bit address field (no carry: < 227 KB), so
+          // one add per descriptor instead of a shift / mask / or chain on the (slow) uniform datapath before every MMA
+          const uint64_t ad0 = make_b_desc(a_addr), bd0 = make_b_desc(b_addr);
+#pragma unroll
+          for (int ks = 0; ks < KBLK / 16; ++ks) {
+            tc_mma_ss(d_base, ad0 + (uint64_t)(2 * ks), bd0 + (uint64_t)(2 * ks), idesc, accum);
+            accum = 1;
+          }
+          tc_commit(&S.empty[st_cur]);
+          if (!hold) tc_commit(&S.a_empty[a_cur]);
+          TR2(i * 16 + 4 + kb * 3);
         }
         if (!hold) { ai = a_i; aph = a_p; }
         if (sgm.kind != K_MID) tc_commit(&S.d_ready[slot]);
@@ -1512,8 +1568,8 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
     g_timing.pair_rows.push_back(n_rows);
     DGDM_CUDA(cudaEventRecord(e0, s));
   }
-  if (two_tile && f16) tc_trunk2_kernel<true><<<grid, NTHREADS, smem2_bytes(), s>>>(P);
-  else if (two_tile) tc_trunk2_kernel<false><<<grid, NTHREADS, smem2_bytes(), s>>>(P);
+  if (two_tile && f16) tc_trunk2_kernel<true><<<grid, NTHREADS2, smem2_bytes(), s>>>(P);
+  else if (two_tile) tc_trunk2_kernel<false><<<grid, NTHREADS2, smem2_bytes(), s>>>(P);
   else if (P.x3 && f16) tc_trunk_kernel<true, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else if (P.x3) tc_trunk_kernel<true, false><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else if (f16) tc_trunk_kernel<false, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);

@@ -26,6 +26,13 @@ __device__ __forceinline__ bool try_wait(uint64_t* b, uint32_t parity) {
                : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking poll (try_wait may suspend the thread for a while before it returns false)
+__device__ __forceinline__ bool test_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -87,11 +94,26 @@ __global__ void __launch_bounds__(NT, 1) k(Params P) {
 
   if (warp == 4 && rank == 0) {
     if (lane == 0) {
+      // mode & 32: the issuer-side work of the real kernel between k-blocks, selected by the bits of `pace`
+      const int ov = (P.mode & 32) ? P.pace : 0;
       const long long t0 = clock64();
-      for (int it = 0; it < P.iters; ++it) {
+      if (P.mode & 8) { while (clock64() - t0 < (long long)P.iters * 4 * 128) { } }
+      if (ov) {   // complete phase 0 of ring_bar[2], ring_bar[3] so that parity-0 waits on them succeed at once
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&ring_bar[2])) : "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&ring_bar[3])) : "memory");
+      }
+      uint32_t sink = 0;
+      for (int it = 0; it < ((P.mode & 8) ? 0 : P.iters); ++it) {
+        if ((ov & 128) && (it & 1)) goto mmas;          // bit 7: the sync work only every other k-block (8 MMAs per round)
+        if (ov & 1) { while (!try_wait(&ring_bar[2], 0)) { } while (!try_wait(&ring_bar[3], 0)) { } }
+        if (ov & 32) { while (!try_wait(&ring_bar[2], 0)) { } }
+        if (ov & 2) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ov & 4) { sink += test_wait(&ring_bar[2], 0); sink += test_wait(&ring_bar[3], 0); }
+      mmas:
+        const uint32_t rot = (ov & 16) ? (uint32_t)(it & 1) * 0u + (uint32_t)(it % 3 == 7) : 0u;   // runtime value, always 0
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = sw128(s32(sA) + ks * 32), bd = sw128(s32(sB) + ks * 32);
+          const uint64_t ad = sw128(s32(sA) + rot * 16384 + ks * 32), bd = sw128(s32(sB) + rot * 16384 + ks * 32);
           const uint32_t acc = (it | ks) ? 1u : 0u;
           if (NCTA == 2)
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -99,6 +121,16 @@ __global__ void __launch_bounds__(NT, 1) k(Params P) {
           else
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                          ::"r"(tm), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+        }
+        if ((ov & 128) && !(it & 1)) continue;
+        if (ov & 64) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&ring_bar[0])) : "memory");
+        if (ov & 8) {
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&ring_bar[0])) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&ring_bar[1])) : "memory");
+        }
+        if (P.mode & 16) {                       // extra commits per 4 MMAs (to barriers nobody waits on)
+          for (int c = 0; c < P.pace; ++c)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&ring_bar[c & 3])) : "memory");
         }
       }
       if (NCTA == 2)
@@ -108,6 +140,7 @@ __global__ void __launch_bounds__(NT, 1) k(Params P) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar)) : "memory");
       while (!try_wait(&bar, 0)) { }
       P.cycles[blockIdx.x / NCTA] = clock64() - t0;
+      if (sink == 0xdeadbeefu) P.cycles[1028] = 1;
     }
   } else if (warp == 5 && (P.mode & 1)) {
     // weight-refill traffic: 16 KB per 4 MMAs per CTA (2-CTA: each CTA stages its half) or 32 KB (1-CTA), 4 in flight
@@ -115,7 +148,7 @@ __global__ void __launch_bounds__(NT, 1) k(Params P) {
       const uint32_t bytes = NCTA == 2 ? 16384u : 32768u;   // 1-CTA: two 16 KB copies per step
       uint32_t ph[4] = {0, 0, 0, 0};
       int n = 0;
-      for (int it = 0; !try_wait(&bar, 0); ++it) {
+      for (int it = 0; !test_wait(&bar, 0); ++it) {
         const int s = it & 3;
         if (it >= 4) { while (!try_wait(&ring_bar[s], ph[s])) { } ph[s] ^= 1; }
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&ring_bar[s])), "r"(bytes) : "memory");
@@ -134,7 +167,7 @@ __global__ void __launch_bounds__(NT, 1) k(Params P) {
     // the barrier is polled every 8 rounds, `pace` dependent FMAs between rounds set the rate
     int n = 0;
     float dummy = (float)threadIdx.x;
-    while (!try_wait(&bar, 0)) {
+    while (!test_wait(&bar, 0)) {
       for (int rep = 0; rep < 8; ++rep) {
         const int row = ((warp - 6) * 32 + lane + rep * 13) & 127;
 #pragma unroll
@@ -148,7 +181,7 @@ __global__ void __launch_bounds__(NT, 1) k(Params P) {
   } else if (warp < 4 && (P.mode & 4)) {
     int n = 0;
     uint32_t acc = 0;
-    while (!try_wait(&bar, 0)) {
+    while (!test_wait(&bar, 0)) {
       for (int rep = 0; rep < 8; ++rep) {
         uint32_t r[16];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -245,9 +278,28 @@ int main() {
   }
   // 2. rate
   const int iters = 4096;
-  for (int ncta = 1; ncta <= 2; ++ncta)
-    for (int mode = 0; mode < 8; ++mode)
-      for (int pace = 0; pace <= ((mode & 2) ? 600 : 0); pace += 200) {
+  for (int commits = 0; commits <= 4; ++commits) {
+    CK(cudaMemset(dc, 0, 2048 * 8));
+    Params P{da, db, nullptr, src, dc, iters, 16, 0, commits};
+    if (launch<1>(P, sms, smem)) return 1;
+    std::vector<long long> c(2048);
+    CK(cudaMemcpy(c.data(), dc, 2048 * 8, cudaMemcpyDeviceToHost));
+    double cyc = 0; for (int i = 0; i < sms; ++i) cyc += (double)c[i];
+    printf("1-CTA M=128, %d tcgen05.commit per 4 MMAs -> %.1f cycles/MMA\n", commits, cyc / sms / (iters * 4));
+  }
+  for (int ov : {0, 1 + 2 + 8, 32 + 2 + 64, 128 + 1 + 2 + 8, 128 + 32 + 2 + 64, 32 + 2, 64, 1 + 2 + 64, 32 + 2 + 8}) {
+    CK(cudaMemset(dc, 0, 2048 * 8));
+    Params P{da, db, nullptr, src, dc, iters, 32, 0, ov};
+    if (launch<1>(P, sms, smem)) return 1;
+    std::vector<long long> c(2048);
+    CK(cudaMemcpy(c.data(), dc, 2048 * 8, cudaMemcpyDeviceToHost));
+    double cyc = 0; for (int i = 0; i < sms; ++i) cyc += (double)c[i];
+    printf("1-CTA M=128, issuer overhead per %d MMAs [%s%s%s%s%s%s%s] -> %.1f cycles/MMA\n", (ov & 128) ? 8 : 4, (ov & 32) ? "1 try_wait " : "", (ov & 64) ? "1 commit " : "", (ov & 1) ? "2 try_wait " : "", (ov & 2) ? "fence " : "",
+           (ov & 4) ? "2 test_wait " : "", (ov & 8) ? "2 commit " : "", (ov & 16) ? "runtime-desc " : "", cyc / sms / (iters * 4));
+  }
+  for (int ncta = 1; ncta <= 1; ++ncta)
+    for (int mode : {0})
+      for (int pace = 0; pace <= ((mode & 2) ? 90 : 0); pace += 30) {
       CK(cudaMemset(dc, 0, 2048 * 8));
       Params P{da, db, nullptr, src, dc, iters, mode, ncta == 2, pace};
       const int grid = ncta == 2 ? (sms / 2) * 2 : sms;
@@ -257,8 +309,8 @@ int main() {
       double cyc = 0; int ncl = grid / ncta;
       for (int i = 0; i < ncl; ++i) cyc += (double)c[i];
       cyc /= ncl;
-      printf("%d-CTA M=%d: %s%s%s(pace %d) -> %.1f cycles/MMA (ideal 128) | refill %.1f B/clk, st.shared %.1f B/clk, tcgen05.ld %.1f B/clk\n",
-             ncta, 128 * ncta, (mode & 1) ? "+refill " : "", (mode & 2) ? "+st.shared " : "", (mode & 4) ? "+tcgen05.ld " : "", pace,
+      printf("%d-CTA M=%d%s: %s%s%s(pace %d) -> %.1f cycles/MMA (ideal 128) | refill %.1f B/clk, st.shared %.1f B/clk, tcgen05.ld %.1f B/clk\n",
+             ncta, 128 * ncta, (mode & 8) ? " NO MMA" : "", (mode & 1) ? "+refill " : "", (mode & 2) ? "+st.shared " : "", (mode & 4) ? "+tcgen05.ld " : "", pace,
              cyc / (iters * 4), (double)c[1024] * (ncta == 2 ? 16384 : 32768) / cyc, (double)c[1025] * 6 * 32 * 128 / cyc,
              (double)c[1026] * 4 * 32 * 64 / cyc);
     }
