@@ -62,12 +62,11 @@ constexpr int NEPI = 16;                       // epilogue warps: 4 per TMEM lan
 constexpr int NTHREADS = (NEPI + 2) * 32;      // + producer warp + MMA warp
 constexpr int MAX_SEG = 20;
 // two-tile single-pass kernel (tc_trunk2_kernel)
-constexpr int NA2 = 5;                         // A-operand ring: k-block slots of 128 rows x 128 B
-constexpr int NW2 = 4;                         // weight ring stages
-constexpr int AKB_BYTES = 128 * 128;           // one A k-block: 16 KB
+constexpr int NS2 = 4;                         // operand ring: one stage per k-block of a segment = [weight tile 32 KB | A k-block 16 KB]
+constexpr int AKB_BYTES = 128 * 128;           // one A k-block: 128 rows x 128 B
+constexpr int STAGE2_BYTES = 256 * KBLK * 2 + AKB_BYTES;   // 48 KB (a multiple of 1024: both parts stay swizzle-aligned)
 constexpr int MAX_ITEMS = 44;                  // work items per tile pair and role: bit 7 = tile slot, bits 0..6 = segment
 constexpr int IT_A1 = 0x7E;                    // item codes 0x7E / 0x7F: build the layer-1 operand, K-half 0 / 1
-constexpr int NTHREADS2 = (NEPI + 3) * 32;     // two-tile kernel: + producer warp + one MMA issuer warp per tile slot
 constexpr int MAX_CTAS2 = 160;                 // mask scratch is sized for this many CTAs
 constexpr int MASK_WORDS = 16 + 7 * 8;         // layer 1 up to 512 wide + 7 layers of 256
 
@@ -144,6 +143,12 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok;
+}
+// One poller per warp: 32 lanes (x 16 warps) hammering the same mbarrier word serialise on it.  Lane 0 polls, the
+// warp reconverges (__syncwarp orders the other lanes' later accesses after lane 0's acquire).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int* err, int code) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, err, code);
+  __syncwarp();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -868,22 +873,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 // MMA per product the chain (~1000 cycles + fill) is half of a layer's 2048 cycles of tensor work: 0.70 of roofline.
 // A second, independent tile hides it, but does not fit in TMEM next to TS-mode operands (2 x (128 + 256) columns).
 // Here TMEM holds only the two fp32 accumulators (2 x 256 columns); the activations go through shared memory (SS-mode
-// MMAs): the epilogue warps convert one tile's accumulator into 16 KB k-blocks of a small shared-memory RING (canonical
-// K-major SWIZZLE_128B, the same image as a weight tile) while the tensor pipe works on the other tile.  The ReLU sign
-// bits no longer fit in shared memory (2 x 36 KB) and live in a per-CTA global scratch (L2 resident; a thread only ever
+// MMAs): while the tensor pipe works on one tile, the epilogue warps convert the other tile's accumulator into the A
+// k-blocks of its next segment (canonical K-major SWIZZLE_128B, the same image as a weight tile).  The ReLU sign bits
+// no longer fit in shared memory (2 x 36 KB) and live in a per-CTA global scratch (L2 resident; a thread only ever
 // reads back words it wrote itself).
 //
-//   warp 16   producer: weight tiles of the MMA work list -> NW2-stage ring (cp.async.bulk)
-//   warp 17   MMA issuer: walks the MMA work list (tile slot, segment); per k-block waits for the A ring slot and the
-//             weight stage, issues 4 tcgen05.mma (SS), commits both slots free; commits d_ready[slot] per segment;
-//             waits d_free[slot] before overwriting an accumulator
+// What sets the pace is the ISSUING THREAD, not the pipe or shared memory (scripts/microbench/mma_2cta.cu): an MMA is
+// taken from the thread only when the pipe can start it, so the pipe is busy only while the thread sits at its next
+// tcgen05.mma, and every barrier operation between two groups of four MMAs beyond ~65 cycles of slack is lost tensor
+// time (try_wait ~50, tcgen05.commit ~55 cycles each: two waits + two polls + two commits per k-block -> 186 cycles
+// per MMA instead of 128).  Hence ONE ring whose stage holds a k-block of BOTH operands: one wait and one commit per
+// k-block.  A segment is exactly NS2 = 4 k-blocks, so stage index = k-block index and every barrier flips once per
+// work item.
+//
+//   warp 16   producer: the weight tile of every (item, k-block) of the MMA work list -> stage[kb].W (cp.async.bulk)
+//   warp 17   MMA issuer: walks the MMA work list (tile slot, segment); waits d_free[slot] before overwriting an
+//             accumulator; per k-block waits full[kb], issues 4 tcgen05.mma (SS), commits empty[kb]; commits d_ready[slot]
 //   warps 0-15 epilogue: walk the epilogue work list; per item wait d_ready[slot], tcgen05.ld the accumulator, release it
-//             (d_free) as soon as the last column is in registers, convert, write A k-blocks into the ring
-//             (st.shared + fence.proxy.async + arrive a_full), sign bits to the scratch
-// The two lists (host, tc2_schedule) interleave the tiles so that the ring is FIFO on both sides and no wait is circular.
+//             (d_free) as soon as the last column is in registers, convert, and write the A k-blocks of the tile's next
+//             segment into stage[kb].A (wait empty[kb]; st.shared + fence.proxy.async; arrive full[kb]); sign bits to the
+//             scratch.  full[kb] completes on the 16 epilogue arrivals + the producer's arrive.expect_tx + the bytes.
+// The two lists (host, tc2_schedule) interleave the tiles so that both sides fill / drain the ring in the same order
+// and no wait is circular.  3D: the two N-halves of the last backward GEMM read the same A operand; the second half's
+// stages are the same physical stages, so the epilogue only re-arrives on them (the A part is left in place) while the
+// producer refills the W part.
 // =============================================================================================
 struct Smem2 {
-  uint64_t full[NW2], empty[NW2], a_full[NA2], a_empty[NA2], d_ready[2], d_free[2], turn[2];
+  uint64_t full[NS2], empty[NS2], d_ready[2], d_free[2];
   uint32_t tmem_base, pad_;
   alignas(16) float bias[7][256];
   alignas(16) float w_out[3][256];
@@ -894,27 +910,25 @@ struct Smem2 {
 
 #ifdef DGDM_TRUNK_TRACE
 // CTA 0, second tile pair: issuer stamps at item*16 + k, epilogue warp 0 at 2048 + item*16 + k (scripts/dev/trunk2_timeline.py)
-#define TR2(slot_) do { if (blockIdx.x == 0 && t == 1 && lane == 0 && (warp == 0 || warp >= NEPI + 1)) g_trace[slot_] = clock64(); } while (0)
+#define TR2(slot_) do { if (blockIdx.x == 0 && t == 1 && lane == 0 && (warp == 0 || warp == NEPI + 1)) g_trace[slot_] = clock64(); } while (0)
 #else
 #define TR2(slot_) do { } while (0)
 #endif
 
 template <bool F16>
-__global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_constant__ TcParams P) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* wring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* aring = wring + NW2 * WTILE_BYTES;
-  Smem2& S = *reinterpret_cast<Smem2*>(aring + NA2 * AKB_BYTES);
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Smem2& S = *reinterpret_cast<Smem2*>(ring + NS2 * STAGE2_BYTES);
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < NW2; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    for (int s = 0; s < NA2; ++s) { mbar_init(&S.a_full[s], NEPI); mbar_init(&S.a_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&S.d_ready[s], 1); mbar_init(&S.d_free[s], NEPI); mbar_init(&S.turn[s], 1); }
+    for (int s = 0; s < NS2; ++s) { mbar_init(&S.full[s], NEPI + 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&S.d_ready[s], 1); mbar_init(&S.d_free[s], NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 7 * 256; i += NTHREADS2) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256] * (F16 ? F16_SA : 1.f);
-  for (int i = tid; i < 3 * 256; i += NTHREADS2) S.w_out[i / 256][i % 256] = P.w_out[i];
+  for (int i = tid; i < 7 * 256; i += NTHREADS) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256] * (F16 ? F16_SA : 1.f);
+  for (int i = tid; i < 3 * 256; i += NTHREADS) S.w_out[i / 256][i % 256] = P.w_out[i];
   if (tid < 3) S.b_out[tid] = P.b_out[tid];
   if (warp == NEPI + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
@@ -931,7 +945,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
   if (warp == NEPI) {
     // =============================== producer ===============================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t phase = 0;
       for (int t = 0; t < pairs_mine; ++t) {
         const bool has1 = 2 * t + 1 < tiles_mine;
         for (int i = 0; i < P.n_m; ++i) {
@@ -940,42 +954,18 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
           const Seg sgm = P.seg[it & 0x7Fu];
           const uint32_t tile_bytes = (uint32_t)sgm.n_rows * 128u;
           for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&S.empty[stage], phase ^ 1, P.err, 1);
-            mbar_arrive_expect_tx(&S.full[stage], tile_bytes);
+            mbar_wait(&S.empty[kb], phase ^ 1, P.err, 1);
+            mbar_arrive_expect_tx(&S.full[kb], tile_bytes);
             // image order inside a segment: kb0.hi, kb0.lo, kb1.hi, ...; the single-pass modes read the hi parts
-            bulk_g2s(wring + stage * WTILE_BYTES, P.img + sgm.img_off + (size_t)(kb * 2) * tile_bytes, tile_bytes, &S.full[stage]);
-            if (++stage == NW2) { stage = 0; phase ^= 1; }
+            bulk_g2s(ring + kb * STAGE2_BYTES, P.img + sgm.img_off + (size_t)(kb * 2) * tile_bytes, tile_bytes, &S.full[kb]);
           }
+          phase ^= 1;
         }
       }
     }
-  } else if (warp == NEPI + 1 || warp == NEPI + 2) {
-    // =============================== MMA issuers (whole warp, uniform; lane 0 issues) ===============================
-    // One issuer warp per tile slot.  The tensor pipe takes MMAs one at a time from a thread (issuing four into an idle
-    // pipe takes ~480 cycles), so whatever a single issuer does between k-blocks -- barrier waits, fences, commits -- is
-    // lost tensor time; with two issuers the other slot's MMAs fill those gaps.  Both walk the same work list and keep
-    // the same ring counters (the producer fills the weight ring, the epilogue the A ring, in list order), each issues
-    // only its own slot's items.  Inside an item the next k-block's barriers are polled before the current k-block's
-    // MMAs are issued, so the answers arrive while the thread is blocked in the issue.
-    // Parity waits are only sound while a waiter is at most one phase ahead of its barrier, and an issuer that skips the
-    // other slot's items could run further ahead than that.  So the list is handed over item by item: an issuer starts
-    // the waits of its item only after the other one has PASSED the waits of the preceding item (turn[]; signalled before
-    // that item's last four MMAs are issued, so the hand-over itself costs the tensor pipe nothing).
-    const uint32_t my_slot = (uint32_t)(warp - (NEPI + 1));
-    uint32_t stage = 0, phase = 0, ai = 0, aph = 0, df_ph = 0, turn_ph = 0;
-    int prev_slot = -1;                           // slot of the previous valid item of the list walk
-    // slot of the valid item that follows item i of pair t (-1: none)
-    auto next_slot = [&](int t, int i) -> int {
-      for (int tt = t; tt < pairs_mine; ++tt) {
-        const bool h1 = 2 * tt + 1 < tiles_mine;
-        for (int j = (tt == t ? i + 1 : 0); j < P.n_m; ++j) {
-          const int sl = P.m_items[j] >> 7;
-          if (sl && !h1) continue;
-          return sl;
-        }
-      }
-      return -1;
-    };
+  } else if (warp == NEPI + 1) {
+    // =============================== MMA issuer (whole warp, uniform; lane 0 issues) ===============================
+    uint32_t phase = 0, df_ph = 0;
     for (int t = 0; t < pairs_mine; ++t) {
       const bool has1 = 2 * t + 1 < tiles_mine;
       for (int i = 0; i < P.n_m; ++i) {
@@ -983,58 +973,33 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
         const uint32_t slot = it >> 7, sg = it & 0x7Fu;
         if (slot && !has1) continue;
         const Seg sgm = P.seg[sg];
-        // 3D: the two N-halves of the last backward GEMM read the same operand; the first one keeps the ring slots
-        const bool hold = sgm.kind == K_LAST && (int)sg != P.n_seg - 1;
-        const int before = prev_slot;
-        prev_slot = (int)slot;
-        if (slot != my_slot) {                   // the other issuer's item: advance the ring counters past it
-          stage += 4; if (stage >= NW2) { stage -= NW2; phase ^= 1; }      // (NW2 = 4: same stage, other phase)
-          if (!hold) { ai += 4; if (ai >= NA2) { ai -= NA2; aph ^= 1; } }
-          continue;
-        }
-        if (before >= 0 && before != (int)my_slot) {      // hand-over from the other issuer
-          mbar_wait(&S.turn[my_slot], turn_ph, P.err, 7);
-          turn_ph ^= 1u;
-        }
-        const bool hand_over = next_slot(t, i) == (int)(my_slot ^ 1u);
         TR2(i * 16 + 0);
         if (!sgm.accum) {                        // this segment overwrites the accumulator: the epilogue must have read it
-          mbar_wait(&S.d_free[slot], (df_ph & 1u) ^ 1u, P.err, 5);
-          df_ph ^= 1u;
-          tc_fence_after();
+          mbar_wait(&S.d_free[slot], ((df_ph >> slot) & 1u) ^ 1u, P.err, 5);
+          df_ph ^= 1u << slot;
         }
         TR2(i * 16 + 1);
         const uint32_t d_base = slot * 256u;
         const uint32_t idesc = make_idesc<F16>(sgm.n_rows);
-        uint32_t accum = sgm.accum, a_i = ai, a_p = aph, hA = 0, hW = 0;
+        uint32_t accum = sgm.accum;
+#pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-          if (!hA) mbar_wait(&S.a_full[a_i], a_p, P.err, 2);
-          TR2(i * 16 + 2 + kb * 3);
-          if (!hW) mbar_wait(&S.full[stage], phase, P.err, 3);
+          mbar_wait(&S.full[kb], phase, P.err, 3);
           tc_fence_after();
           TR2(i * 16 + 3 + kb * 3);
-          if (kb == 3 && hand_over && lane == 0) mbar_arrive(&S.turn[my_slot ^ 1u]);   // all waits of this item are behind us
-          const uint32_t a_addr = smem_u32(aring + a_i * AKB_BYTES), b_addr = smem_u32(wring + stage * WTILE_BYTES);
-          const uint32_t st_cur = stage, a_cur = a_i;
-          if (++stage == NW2) { stage = 0; phase ^= 1; }
-          if (++a_i == NA2) { a_i = 0; a_p ^= 1; }
-          if (kb < 3) {                           // poll the next k-block's barriers now (see above)
-            hA = mbar_test(&S.a_full[a_i], a_p);
-            hW = mbar_test(&S.full[stage], phase);
-          }
           // descriptors of the four K = 16 steps: + 32 bytes = + 2 in the 14-bit address field (no carry: < 227 KB), so
-          // one add per descriptor instead of a shift / mask / or chain on the (slow) uniform datapath before every MMA
-          const uint64_t ad0 = make_b_desc(a_addr), bd0 = make_b_desc(b_addr);
+          // one add per descriptor instead of a shift / mask / or chain on the uniform datapath before every MMA
+          const uint32_t b_addr = smem_u32(ring + kb * STAGE2_BYTES);
+          const uint64_t bd0 = make_b_desc(b_addr), ad0 = make_b_desc(b_addr + 256 * KBLK * 2);
 #pragma unroll
           for (int ks = 0; ks < KBLK / 16; ++ks) {
             tc_mma_ss(d_base, ad0 + (uint64_t)(2 * ks), bd0 + (uint64_t)(2 * ks), idesc, accum);
             accum = 1;
           }
-          tc_commit(&S.empty[st_cur]);
-          if (!hold) tc_commit(&S.a_empty[a_cur]);
+          tc_commit(&S.empty[kb]);
           TR2(i * 16 + 4 + kb * 3);
         }
-        if (!hold) { ai = a_i; aph = a_p; }
+        phase ^= 1;
         if (sgm.kind != K_MID) tc_commit(&S.d_ready[slot]);
         TR2(i * 16 + 14);
       }
@@ -1045,27 +1010,39 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int l1_hw = P.H1 / 16;
-    uint32_t ei = 0, eph = 0, dr_ph = 0;
+    uint32_t ekb = 0, eph = 0, dr_ph = 0;        // next stage to fill (= k-block index of the production), its phase
     uint16_t* const mask_cta = P.mask_scratch + (size_t)blockIdx.x * 2 * (2 * MASK_WORDS) * TILE_M + row;
 
-    // this warp's 32 rows x 16 features of the next A k-block -> ring slot (canonical K-major SWIZZLE_128B)
+    // this warp's 32 rows x 16 features of the next A k-block -> stage[ekb].A (canonical K-major SWIZZLE_128B);
+    // `write` = false: the operand is already there (3D, second N-half of the last GEMM): only hand the stage over again
     [[maybe_unused]] int tr_i = 0, tr_t = 0, tr_kb = 0;
-    auto put_kb = [&](const uint32_t (&hi)[8]) {
-      mbar_wait(&S.a_empty[ei], eph ^ 1u, P.err, 6);
+    auto put_kb = [&](const uint32_t (&hi)[8], bool write) {
+      mbar_wait(&S.empty[ekb], eph ^ 1u, P.err, 6);
 #ifdef DGDM_TRUNK_TRACE
       { const int t = tr_t; TR2(2048 + tr_i * 16 + 8 + (tr_kb & 3)); }
 #endif
-      uint8_t* dst = aring + ei * AKB_BYTES + row * 128;
-      const int sw = row & 7;
-      *reinterpret_cast<uint4*>(dst + (((2 * hq) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(dst + (((2 * hq + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.a_full[ei]);
+      if (write) {
+        uint8_t* dst = ring + ekb * STAGE2_BYTES + 256 * KBLK * 2 + row * 128;
+        const int sw = row & 7;
+        *reinterpret_cast<uint4*>(dst + (((2 * hq) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + (((2 * hq + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      }
+      // One proxy fence per ITEM (after the fourth k-block), then the four arrivals: fence.proxy.async costs the warp ~400
+      // cycles, four of them per item made the epilogue the slowest role.  Tried instead: st.async (STAS, needs a cluster
+      // launch) with transaction-count completion and no fence: 6600 cycles per item; the fence from lane 0 only, per
+      // k-block: no gain.
+      if (ekb == NS2 - 1) {
+        if (write) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < NS2; ++k) mbar_arrive(&S.full[k]);
+        }
+      }
 #ifdef DGDM_TRUNK_TRACE
       { const int t = tr_t; TR2(2048 + tr_i * 16 + 2 + (tr_kb & 3)); ++tr_kb; }
 #endif
-      if (++ei == NA2) { ei = 0; eph ^= 1u; }
+      if (++ekb == NS2) { ekb = 0; eph ^= 1u; }
     };
 
     for (int t = 0; t < pairs_mine; ++t) {
@@ -1124,7 +1101,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
             if (kb + 1 < 4) load_z(kh * 256 + (kb + 1) * 64 + hq * 16, zb[(kb + 1) & 1]);
             uint32_t hi[8], lo[8];
             relu_split16<false, F16>(zb[kb & 1], hi, lo);
-            put_kb(hi);
+            put_kb(hi, true);
             __stcg(mk + (kh * 16 + kb * 4 + hq) * TILE_M, (uint16_t)sign_bits16(hi));
           }
           TR2(2048 + i * 16 + 6);
@@ -1169,7 +1146,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
             }
             uint32_t hi[8], lo[8];
             relu_split16<false, F16>(z, hi, lo);
-            put_kb(hi);
+            put_kb(hi, true);
             __stcg(mk + (mbase + kb * 4 + hq) * TILE_M, (uint16_t)sign_bits16(hi));
           }
           TR2(2048 + i * 16 + 6);
@@ -1193,7 +1170,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
             for (int k = 0; k < 16; ++k) v[k] = (bits[kb] >> mask_pos(k)) & 1u ? unscale<F16>(rr[kb & 1][k]) : 0.f;
             uint32_t hi[8], lo[8];
             split_pack<false, F16>(v, hi, lo);
-            put_kb(hi);
+            put_kb(hi, true);
           }
           TR2(2048 + i * 16 + 6);
         } else {
@@ -1260,7 +1237,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
                 }
                 uint32_t hi[8], lo[8];
                 split_pack<false, F16>(v, hi, lo);
-                put_kb(hi);
+                put_kb(hi, true);
               }
             }
             TR2(2048 + i * 16 + 6);
@@ -1272,6 +1249,11 @@ __global__ void __launch_bounds__(NTHREADS2, 1) tc_trunk2_kernel(const __grid_co
             for (int kb = 0; kb < 4; ++kb) bits[kb] = __ldcg(mk + (sgm.half * 16 + kb * 4 + hq) * TILE_M);
             wait_d();
             TR2(2048 + i * 16 + 1);
+            if (code != P.n_seg - 1) {                // 3D, first N-half: hand the same operand over for the second half
+              const uint32_t none[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll 1
+              for (int kb = 0; kb < 4; ++kb) put_kb(none, false);
+            }
             if (P.G == 1) {                           // explicit-row mode: the row IS the pair; store it directly
 #pragma unroll 1
               for (int kb = 0; kb < 4; ++kb) {
@@ -1421,7 +1403,7 @@ Plan make_plan(const dgdm_dyn_weights* w, int H1) {
 }
 
 size_t smem_bytes() { return 1024 + (size_t)NSTAGE * WTILE_BYTES + sizeof(Smem); }
-size_t smem2_bytes() { return 1024 + (size_t)NW2 * WTILE_BYTES + (size_t)NA2 * AKB_BYTES + sizeof(Smem2); }
+size_t smem2_bytes() { return 1024 + (size_t)NS2 * STAGE2_BYTES + sizeof(Smem2); }
 constexpr size_t MASK_SCRATCH_BYTES = (size_t)MAX_CTAS2 * 2 * (2 * MASK_WORDS) * TILE_M * sizeof(uint16_t);
 
 // DGDM_TRUNK2=1 runs the single-pass modes on the two-tile kernel.  Off by default: it is parity-green but not faster
@@ -1568,8 +1550,8 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
     g_timing.pair_rows.push_back(n_rows);
     DGDM_CUDA(cudaEventRecord(e0, s));
   }
-  if (two_tile && f16) tc_trunk2_kernel<true><<<grid, NTHREADS2, smem2_bytes(), s>>>(P);
-  else if (two_tile) tc_trunk2_kernel<false><<<grid, NTHREADS2, smem2_bytes(), s>>>(P);
+  if (two_tile && f16) tc_trunk2_kernel<true><<<grid, NTHREADS, smem2_bytes(), s>>>(P);
+  else if (two_tile) tc_trunk2_kernel<false><<<grid, NTHREADS, smem2_bytes(), s>>>(P);
   else if (P.x3 && f16) tc_trunk_kernel<true, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else if (P.x3) tc_trunk_kernel<true, false><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else if (f16) tc_trunk_kernel<false, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);

@@ -2,8 +2,8 @@
 
     DGDM_NVCC_EXTRA=-DDGDM_TRUNK_TRACE python -m dgdm_b200.build -f
     python scripts/dev/trunk2_timeline.py {bf16|fp16} [2d|3d]
-Trace slots (dynamics_tc.cu, TR2()): issuer item i at i*16 + {0: start, 1: accumulator free, 2+3kb: A k-block ready,
-3+3kb: weight stage ready, 4+3kb: k-block issued + committed, 14: end}; epilogue warp 0 at 2048 + i*16 + {0: start,
+Trace slots (dynamics_tc.cu, TR2()): issuer item i at i*16 + {0: start, 1: accumulator free, 3+3kb: stage kb full,
+4+3kb: k-block issued + committed, 14: end}; epilogue warp 0 at 2048 + i*16 + {0: start,
 1: accumulator complete (d_ready), 2..5: k-block kb handed over, 6: end, 8..11: ring slot for k-block kb free}.
 """
 import ctypes as C
@@ -45,15 +45,15 @@ n_m = (34 if is3d else 30)
 n_e = (36 if is3d else 32)
 t0 = min(int(v) for v in tr[:4096] if v > 0)
 print(f"{prec} {'3D' if is3d else '2D'} two-tile kernel; cycles relative to the first stamp of the pair")
-print("MMA issuer items: start | wait d_free | per k-block: wait A, wait W, issue | end")
+print("MMA issuer items: start | wait d_free | per k-block: wait full, issue + commit | dur")
 prev = None
 for i in range(n_m):
     r = tr[i * 16: i * 16 + 16]
     if r[14] == 0:
         continue
-    kb = [(int(r[2 + 3 * k] - (r[1] if k == 0 else r[4 + 3 * (k - 1)])), int(r[3 + 3 * k] - r[2 + 3 * k]), int(r[4 + 3 * k] - r[3 + 3 * k])) for k in range(4)]
+    kb = [(int(r[3 + 3 * k] - (r[1] if k == 0 else r[4 + 3 * (k - 1)])), int(r[4 + 3 * k] - r[3 + 3 * k])) for k in range(4)]
     gap = 0 if prev is None else int(r[0] - prev)
-    print(f"  M{i:2d}: start {int(r[0]-t0):7d} (gap {gap:5d}) dfree {int(r[1]-r[0]):5d} | " + " ".join(f"[{a:4d},{w:4d},{s:4d}]" for a, w, s in kb)
+    print(f"  M{i:2d}: start {int(r[0]-t0):7d} (gap {gap:5d}) dfree {int(r[1]-r[0]):5d} | " + " ".join(f"[{w:4d},{s:4d}]" for w, s in kb)
           + f" | dur {int(r[14]-r[0]):5d}")
     prev = r[14]
 print(f"issuer: {int(prev - tr[0])} cycles for the pair = {int(prev - tr[0]) // 2} per tile")
