@@ -465,18 +465,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           for (int j = 0; j < tiles_per_seg; ++j) {
             const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;
             TR(sg * 64 + j * 4 + 0);
-            if (part == 0) {
-              mbar_wait(&S.a_ready[kb], a_phase, P.err, 2);
-              tc_fence_after();
-            }
+            if (part == 0) mbar_wait(&S.a_ready[kb], a_phase, P.err, 2);
             TR(sg * 64 + j * 4 + 1);
             mbar_wait(&S.full[stage], phase, P.err, 3);
             tc_fence_after();
             TR(sg * 64 + j * 4 + 2);
-            const uint32_t b_addr = smem_u32(ring + stage * WTILE_BYTES);
+            // descriptors of the four K = 16 steps: + 32 bytes = + 2 in the 14-bit address field (no carry below 256 KB):
+            // one add per MMA instead of a shift / mask / or chain on the uniform datapath (the issuing thread, not the
+            // tensor pipe, sets the pace between weight tiles: scripts/microbench/mma_2cta.cu)
+            const uint64_t bdesc0 = make_b_desc(smem_u32(ring + stage * WTILE_BYTES));
 #pragma unroll
             for (int ks = 0; ks < KBLK / 16; ++ks) {
-              const uint64_t bdesc = make_b_desc(b_addr + ks * 32);
+              const uint64_t bdesc = bdesc0 + (uint64_t)(2 * ks);
               const uint32_t a_col = (uint32_t)(kb * 64 + ks * 16);            // 16 operand elements = 8 TMEM columns: [hi 8 | lo 8]
               tc_mma_ts(d_base, a_base + a_col, bdesc, idesc, accum);
               accum = 1;
