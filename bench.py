@@ -271,6 +271,7 @@ def run_workload(ctx, wl, precision, steps, warmup, want_clocks=False):
     from dgdm_b200.diffusion import Diffusion
     from dgdm_b200.scheduler import DDIMScheduler
     lib, dev, world, rank = ctx.lib, ctx.dev, ctx.world, ctx.rank
+    wl_name = next(k for k, v in WORKLOADS.items() if v is wl)
     n_cand, P = wl["n_cand"], wl["P"]
     is3d = wl["mode"] == "point_3d"
     n_obj_global = wl["n_obj"] if wl["strong"] else wl["n_obj"] * world
@@ -350,8 +351,10 @@ def run_workload(ctx, wl, precision, steps, warmup, want_clocks=False):
     peak = pk["bf16_sustained"] / (3.0 if x3 else 1.0)
     traffic = None                       # DRAM bytes per launch of this kernel from the committed ncu --set full capture
     tpath = os.path.join(REPO, "profiles", "tc_trunk_traffic.json")
-    if os.path.exists(tpath) and wl is WORKLOADS["c2"]:        # captured on C2 only
-        traffic = json.load(open(tpath)).get("fp32" if x3 else "bf16", {}).get("dram_bytes_per_launch")
+    if os.path.exists(tpath):                                # captured per (workload, mode): see the file's note
+        key = {("c2", True): "fp32", ("c2", False): "bf16"}.get((wl_name, x3)) if wl_name == "c2" else \
+            (f"c3_{precision}" if wl_name == "c3" else None)
+        traffic = json.load(open(tpath)).get(key, {}).get("dram_bytes_per_launch") if key else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
                 "kernel": "tc_trunk_kernel, guidance launches (fused tcgen05 trunk fwd + dgrad + per-pair reduction)",

@@ -16,7 +16,7 @@ sys.path.insert(0, REPO)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c2", choices=["c2", "c2g36", "c3", "c5"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16x3", "bf16", "fp16", "fp32_simt"])
     args = ap.parse_args()
 
     import torch
@@ -25,21 +25,22 @@ def main():
     from dgdm_b200.diffusion import Diffusion
     from dgdm_b200.scheduler import DDIMScheduler
 
-    bench.select_workload(args.workload)
+    wl = bench.WORKLOADS[args.workload]
+    n_obj, n_cand, P = wl["n_obj"], wl["n_cand"], wl["P"]
     dev = torch.device("cuda", 0)
-    is3d = bench.MODE == "point_3d"
-    objs = (syn.objects_3d(bench.N_OBJ) if is3d else syn.objects_2d(bench.N_OBJ)).contiguous()
-    fps = syn.fps_starts(bench.N_OBJ).contiguous() if is3d else None
-    dm = Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(bench.T_TRAIN), bench.T_INF, mode=bench.MODE, num_points=bench.P,
+    is3d = wl["mode"] == "point_3d"
+    objs = (syn.objects_3d(n_obj) if is3d else syn.objects_2d(n_obj)).contiguous()
+    fps = syn.fps_starts(n_obj).contiguous() if is3d else None
+    dm = Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(bench.T_TRAIN), bench.T_INF, mode=wl["mode"], num_points=P,
                    classifier_model=syn.dynamics3d_state_dict(0) if is3d else syn.dynamics2d_state_dict(0),
-                   grid_size=bench.GRID, num_pos=bench.NPOS, object_vertices=objs, object_ids=list(range(bench.N_OBJ)),
+                   grid_size=wl["grid"], num_pos=wl["npos"], object_vertices=objs, object_ids=list(range(n_obj)),
                    fps_starts=fps, precision=args.precision, device=dev)
-    noise = syn.initial_noise(bench.N_CAND, bench.P).to(dev)
-    dm.guided_sample(0, bench.N_CAND, noise, opt_obj=bench.OBJECTIVE)
+    noise = syn.initial_noise(n_cand, P).to(dev)
+    dm.guided_sample(0, n_cand, noise, opt_obj=bench.OBJECTIVE)
     torch.cuda.synchronize()
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        dm.guided_sample(0, bench.N_CAND, noise, opt_obj=bench.OBJECTIVE)
+        dm.guided_sample(0, n_cand, noise, opt_obj=bench.OBJECTIVE)
         torch.cuda.synchronize()
     tot = collections.defaultdict(lambda: [0.0, 0])
     for ev in prof.events():
