@@ -546,3 +546,31 @@ def test_guided_sampling_is_deterministic():
     b = dm.guided_sample(0, 64, noise, opt_obj="clockwise_up")
     assert torch.equal(a["designs"], b["designs"]) and torch.equal(a["scores"], b["scores"])
     assert torch.equal(a["best_ids"], b["best_ids"])
+
+
+# ---------------------------------------------------------------------------------------------- torch.library ops
+def test_torch_library_ops_match_the_python_api():
+    """The custom ops (dgdm_b200/ops.py) drive the same C-ABI entry points as ``Diffusion``: one guided step and the
+    selection through ``torch.ops.dgdm_b200.*`` are bit-identical to the methods."""
+    import dgdm_b200.ops as ops
+    from dgdm_b200 import _lib
+    from dgdm_b200.diffusion import OBJECTIVES
+    objs = syn.objects_2d(2)
+    dm = make2d("fp32", objs, 12, 2)
+    x = syn.initial_noise(8, 14)[..., 0].cuda().repeat(2, 1).contiguous()           # design d = o * 8 + b
+    t = 9
+    hu, hd = ops.register_pack(dm.unet), ops.register_pack(dm.dyn)
+    prec = _lib.PRECISIONS["fp32"]
+    eps = torch.ops.dgdm_b200.unet1d_forward(x, hu, t, prec)
+    assert torch.equal(eps, dm.noise_pred_net(x, t))
+    c0, c1, c2, sq = OBJECTIVES["rotate_clockwise"]
+    grad = torch.ops.dgdm_b200.dyn_guidance(x, dm._obj_dev, hd, dm._t_frac(t), 12, 2, -1.0, 1.0, c0, c1, c2, sq, 1.0, prec)
+    assert torch.equal(grad, dm.guidance(x, t, dm._obj_dev, 1, "rotate_clockwise"))
+    scale = dm.classifier_scale("rotate_clockwise")
+    nxt = torch.ops.dgdm_b200.ddim_guided_update(x, eps, grad, *dm.noise_scheduler.coefficients(t), scale, True)
+    assert torch.equal(nxt, dm.noise_scheduler.guided_step(eps, t, x, grad, scale))
+    scores = torch.randn(3, 40, device="cuda")
+    idx, best = torch.ops.dgdm_b200.best_of_n(scores, 4)
+    i2, b2 = dm.best_of_n(scores, 4)
+    assert torch.equal(idx, i2) and torch.equal(best, b2)
+    ops.release_pack(hu); ops.release_pack(hd)

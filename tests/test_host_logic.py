@@ -253,3 +253,22 @@ def test_cli_normalises_objects_as_the_reference():
     want2[..., 1] = (want2[..., 1] - (-0.05)) / (0.05 - (-0.05)) * 2.0 - 1.0
     assert torch.equal(cli.normalise_objects(v2, False), want2)
     assert torch.equal(v2, torch.from_numpy(np.asarray(v2)))        # input untouched
+
+
+def test_torch_library_ops_are_registered_with_fake_kernels():
+    """the C ABI is also exposed as torch.library custom ops.  On CPU: the schemas exist, the fake (meta)
+    kernels propagate shapes, and a call with CPU tensors fails loudly (no CPU implementation)."""
+    import dgdm_b200.ops  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    ns = torch.ops.dgdm_b200
+    for name in ("unet1d_forward", "dyn_guidance", "ddim_guided_update", "best_of_n"):
+        assert hasattr(ns, name), name
+    with FakeTensorMode():
+        x = torch.empty(6, 14)
+        assert ns.unet1d_forward(x, 0, 9, 1).shape == (6, 14)
+        assert ns.dyn_guidance(x, torch.empty(2, 200), 0, 0.4, 36, 5, -1.0, 1.0, -1.0, 0.0, 0.0, 0.0, 1.0, 1).shape == (6, 14)
+        assert ns.ddim_guided_update(x, x, x, 0.9, 0.4, 0.5, 0.8, 1e-3, True).shape == (6, 14)
+        idx, best = ns.best_of_n(torch.empty(3, 16), 4)
+        assert idx.shape == (3, 4) and idx.dtype == torch.int64 and best.shape == (3, 4)
+    with pytest.raises(RuntimeError):
+        ns.ddim_guided_update(torch.zeros(2, 14), torch.zeros(2, 14), torch.zeros(2, 14), 0.9, 0.4, 0.5, 0.8, 1e-3, True)

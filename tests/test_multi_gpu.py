@@ -53,3 +53,33 @@ def test_candidate_shards_when_fewer_objects_than_ranks(mode):
     rep = _run(w, "--objects", "1" if w == 2 else "5", "--candidates", "64", "--precision", "fp32", "--mode", mode,
                *(["--grid", "36"] if mode == "point" else []))
     assert rep["plan"] == "candidates" and rep["best_ids"]["bit_exact"]
+
+
+def test_diffusion_on_a_non_current_device():
+    """every launch must run in the context and on the stream of the device that owns the tensors.  Build the
+    sampler on cuda:1 while cuda:0 is the process-wide current device and compare with the same run on cuda:0."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, REPO)
+    from dgdm_b200 import synthetic as syn
+    from dgdm_b200.diffusion import Diffusion
+    from dgdm_b200.scheduler import DDIMScheduler
+    torch.cuda.set_device(0)
+    objs, noise = syn.objects_2d(3), syn.initial_noise(8, 14)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        dm = Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(15), 5, mode="point", num_points=14,
+                       classifier_model=syn.dynamics2d_state_dict(0), grid_size=12, num_pos=2, object_vertices=objs,
+                       object_ids=[0, 1, 2], precision="fp32", device=dev)
+        assert torch.cuda.current_device() == 0
+        out = dm.guided_sample(0, 8, noise, opt_obj="rotate_clockwise", top_k=2)
+        assert out["designs"].device == torch.device(dev)
+        data = dm.unguided_sample(noise)                        # scheduler.guided_step on `dev`
+        metrics = dm.denoise_from_data(data, seed=1)            # the add_noise launch on `dev`
+        res = {k: v.cpu() for k, v in out.items()}
+        res["unguided"] = data.cpu()
+        res["metrics"] = torch.tensor([metrics[k] for k in sorted(metrics)])
+        outs.append(res)
+        torch.cuda.synchronize(dev)
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
