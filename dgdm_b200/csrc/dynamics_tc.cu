@@ -134,22 +134,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     }
   }
 }
-// Non-blocking poll (acquire): 1 if the phase with this parity has completed.  try_wait may suspend the thread.
-__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok;
-}
-// One poller per warp: 32 lanes (x 16 warps) hammering the same mbarrier word serialise on it.  Lane 0 polls, the
-// warp reconverges (__syncwarp orders the other lanes' later accesses after lane 0's acquire).
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int* err, int code) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, err, code);
-  __syncwarp();
-}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
