@@ -272,3 +272,26 @@ def test_torch_library_ops_are_registered_with_fake_kernels():
         assert idx.shape == (3, 4) and idx.dtype == torch.int64 and best.shape == (3, 4)
     with pytest.raises(RuntimeError):
         ns.ddim_guided_update(torch.zeros(2, 14), torch.zeros(2, 14), torch.zeros(2, 14), 0.9, 0.4, 0.5, 0.8, 1e-3, True)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """``bench.py --impl reference`` (CPU only): one JSON line with the contract keys, the reference's own sampler as the
+    thing timed when oracle/_ref is present (kind "reference"), else the oracle port (kind "port")."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    have_ref = os.path.exists(os.path.join(repo, "oracle", "_ref", "reference", "generator", "diffusion.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    # other ranks of a torchrun launch exit 0 without work
+    r = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == ""
