@@ -574,3 +574,53 @@ def test_torch_library_ops_match_the_python_api():
     i2, b2 = dm.best_of_n(scores, 4)
     assert torch.equal(idx, i2) and torch.equal(best, b2)
     ops.release_pack(hu); ops.release_pack(hd)
+
+
+# ---------------------------------------------------------------------------------------------- launch chunking, opt-in kernel
+def test_object_chunking_is_invisible():
+    """guided_sample splits a large object set into launches of at most ``max_designs_per_launch`` designs (the guidance
+    workspace holds ~20 KB per design at G = 1125); objects are independent, so the chunked run is bit-identical."""
+    objs = syn.objects_2d(6)
+    noise = syn.initial_noise(16, 14)
+    dm = make2d("fp32", objs, 12, 2)
+    want = dm.guided_sample(0, 16, noise, opt_obj="rotate_clockwise", top_k=3)
+    dm.max_designs_per_launch = 32                                   # 2 objects per launch
+    got = dm.guided_sample(0, 16, noise, opt_obj="rotate_clockwise", top_k=3)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+
+
+_TRUNK2_SCRIPT = r"""
+import sys, torch
+sys.path[:0] = [sys.argv[1], sys.argv[1] + "/tests", sys.argv[1] + "/oracle"]
+from dgdm_b200 import synthetic as syn
+from test_gpu_parity import make2d, make3d
+out = {}
+for prec in ("bf16", "fp16"):
+    dm = make2d(prec, syn.objects_2d(2), 36, 5)
+    x = syn.initial_noise(40, 14)[..., 0].cuda().repeat(2, 1).contiguous()
+    out["2d_" + prec] = dm.guidance(x, 6, dm._obj_dev, 1, "rotate").cpu()
+    out["2d_score_" + prec] = dm.score(x, dm._obj_dev, 1, "rotate_clockwise").cpu()
+    dm3 = make3d(prec, syn.objects_3d(2), syn.fps_starts(2), 9, 3)
+    x3 = syn.initial_noise(24, 42)[..., 0].cuda().repeat(2, 1).contiguous()
+    out["3d_" + prec] = dm3.guidance(x3, 3, dm3._obj_dev, 1, "rotate_clockwise").cpu()
+torch.save(out, sys.argv[2])
+"""
+
+
+def test_two_tile_kernel_opt_in_is_bit_identical(tmp_path):
+    """DGDM_TRUNK2=1 routes the single-pass modes through tc_trunk2_kernel (two tiles in flight, SS-mode operands).  Same
+    operands, same K order, same reduction order: its gradients and scores equal the default kernel's bit for bit."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for flag in ("0", "1"):
+        path = str(tmp_path / f"trunk2_{flag}.pt")
+        r = subprocess.run([sys.executable, "-c", _TRUNK2_SCRIPT, repo, path], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, DGDM_TRUNK2=flag))
+        assert r.returncode == 0, r.stderr[-3000:]
+        res[flag] = torch.load(path)
+    for k in res["0"]:
+        assert torch.equal(res["0"][k], res["1"][k]), (k, float((res["0"][k] - res["1"][k]).abs().max()))
