@@ -54,7 +54,10 @@ constexpr int WTILE_BYTES = 256 * KBLK * 2;    // 32 KB ring slot: 256 rows x 12
 // and gradients -- where it keeps fewer and fewer bits (measured: unscaled fp16 hi+lo operands were 2x LESS accurate
 // than bf16 hi+lo).  So the weight image holds W * SW, activations live in TMEM as a * SA and backward operands as
 // d * GS; the epilogues undo SW with the multiply they already do (forward: fma(D, 1/SW, SA*b)) or one FMUL (backward).
-constexpr float F16_SW = 256.f;                // weights
+constexpr float F16_SW = 256.f;                // weights of the fp16 hi+lo (x3) image; the single-pass fp16 image is unscaled:
+                                               // without a lo part nothing goes subnormal, and the backward epilogue saves
+                                               // its 16 FMULs per k-block (fp16 trunk 0.67 -> see DESIGN.md 4.1)
+template <bool F16, bool X3> constexpr float sw_of() { return (F16 && X3) ? F16_SW : 1.f; }
 constexpr float F16_SA = 64.f;                 // forward activations
 constexpr float F16_GS = 64.f;                 // backward operands (seed); undone by reduce_slots together with SW
 constexpr int NSTAGE = 5;
@@ -222,13 +225,13 @@ __device__ __forceinline__ int pair_obj(int64_t p, int opd, int n_designs, int n
 }
 
 // accumulator word -> value with the weight scale of the fp16 modes removed (see F16_SW)
-template <bool F16>
+template <bool F16, bool X3>
 __device__ __forceinline__ float unscale(uint32_t acc) {
-  return F16 ? __uint_as_float(acc) * (1.f / F16_SW) : __uint_as_float(acc);
+  return (F16 && X3) ? __uint_as_float(acc) * (1.f / F16_SW) : __uint_as_float(acc);
 }
-template <bool F16>
+template <bool F16, bool X3>
 __device__ __forceinline__ float unscale_add(uint32_t acc, float b) {
-  return F16 ? fmaf(__uint_as_float(acc), 1.f / F16_SW, b) : __uint_as_float(acc) + b;
+  return (F16 && X3) ? fmaf(__uint_as_float(acc), 1.f / F16_SW, b) : __uint_as_float(acc) + b;
 }
 
 __device__ __forceinline__ uint32_t cvt_rn_f16x2(float lo_elem, float hi_elem) {
@@ -623,10 +626,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
                 const float4 bb = b4[i4];                // (fp16 modes: SA * b; D = SA * SW * (a . w))
-                z[i4 * 4 + 0] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 0], bb.x);
-                z[i4 * 4 + 1] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 1], bb.y);
-                z[i4 * 4 + 2] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 2], bb.z);
-                z[i4 * 4 + 3] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 3], bb.w);
+                z[i4 * 4 + 0] = unscale_add<F16, X3>(rr[kb & 1][i4 * 4 + 0], bb.x);
+                z[i4 * 4 + 1] = unscale_add<F16, X3>(rr[kb & 1][i4 * 4 + 1], bb.y);
+                z[i4 * 4 + 2] = unscale_add<F16, X3>(rr[kb & 1][i4 * 4 + 2], bb.z);
+                z[i4 * 4 + 3] = unscale_add<F16, X3>(rr[kb & 1][i4 * 4 + 3], bb.w);
               }
               uint32_t hi[8], lo[8];
               relu_split16<X3, F16>(z, hi, lo);
@@ -639,7 +642,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
               const uint32_t bits = S.mask[mbase + kb * 4 + hq][row];
               float v[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = (bits >> mask_pos(i)) & 1u ? unscale<F16>(rr[kb & 1][i]) : 0.f;
+              for (int i = 0; i < 16; ++i) v[i] = (bits >> mask_pos(i)) & 1u ? unscale<F16, X3>(rr[kb & 1][i]) : 0.f;
               TRE(kb, 7);
               store_a(dreg, kb, v);
               TRE(kb, 8);
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
         } else if (!X3 && sgm.kind == K_OUT) {          // (compile-time: only the bf16 instantiation has this form)
           uint32_t rr[8];
           tmem_ld8(d_addr, rr);
-          constexpr float inv_out = F16 ? 1.f / (F16_SA * F16_SW) : 1.f;       // D = SA * SW * (a8 . w_out)
+          constexpr float inv_out = F16 ? 1.f / (F16_SA * sw_of<F16, X3>()) : 1.f;       // D = SA * SW * (a8 . w_out)
           const float l0 = __uint_as_float(rr[0]) * inv_out + S.b_out[0], l1 = __uint_as_float(rr[1]) * inv_out + S.b_out[1],
                       l2 = __uint_as_float(rr[2]) * inv_out + S.b_out[2];
           if (hq == 0 && live && P.logits) {
@@ -722,8 +725,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
                 const float4 bb = b4[i4], a0 = w0[i4], a1 = w1[i4], a2 = w2[i4];
-                const float zz[4] = {unscale_add<F16>(rr[kb & 1][i4 * 4 + 0], bb.x), unscale_add<F16>(rr[kb & 1][i4 * 4 + 1], bb.y),
-                                     unscale_add<F16>(rr[kb & 1][i4 * 4 + 2], bb.z), unscale_add<F16>(rr[kb & 1][i4 * 4 + 3], bb.w)};
+                const float zz[4] = {unscale_add<F16, X3>(rr[kb & 1][i4 * 4 + 0], bb.x), unscale_add<F16, X3>(rr[kb & 1][i4 * 4 + 1], bb.y),
+                                     unscale_add<F16, X3>(rr[kb & 1][i4 * 4 + 2], bb.z), unscale_add<F16, X3>(rr[kb & 1][i4 * 4 + 3], bb.w)};
                 const float wa[4] = {a0.x, a0.y, a0.z, a0.w}, wb[4] = {a1.x, a1.y, a1.z, a1.w}, wc[4] = {a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -1123,10 +1126,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
               const float4 bb = b4[i4];
-              z[i4 * 4 + 0] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 0], bb.x);
-              z[i4 * 4 + 1] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 1], bb.y);
-              z[i4 * 4 + 2] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 2], bb.z);
-              z[i4 * 4 + 3] = unscale_add<F16>(rr[kb & 1][i4 * 4 + 3], bb.w);
+              z[i4 * 4 + 0] = unscale_add<F16, false>(rr[kb & 1][i4 * 4 + 0], bb.x);
+              z[i4 * 4 + 1] = unscale_add<F16, false>(rr[kb & 1][i4 * 4 + 1], bb.y);
+              z[i4 * 4 + 2] = unscale_add<F16, false>(rr[kb & 1][i4 * 4 + 2], bb.z);
+              z[i4 * 4 + 3] = unscale_add<F16, false>(rr[kb & 1][i4 * 4 + 3], bb.w);
             }
             uint32_t hi[8], lo[8];
             relu_split16<false, F16>(z, hi, lo);
@@ -1151,7 +1154,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
             else release_d();
             float v[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = (bits[kb] >> mask_pos(k)) & 1u ? unscale<F16>(rr[kb & 1][k]) : 0.f;
+            for (int k = 0; k < 16; ++k) v[k] = (bits[kb] >> mask_pos(k)) & 1u ? unscale<F16, false>(rr[kb & 1][k]) : 0.f;
             uint32_t hi[8], lo[8];
             split_pack<false, F16>(v, hi, lo);
             put_kb(hi, true);
@@ -1179,7 +1182,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
             uint32_t rr[8];
             tmem_ld8(d_addr, rr);
             release_d();
-            constexpr float inv_out = F16 ? 1.f / (F16_SA * F16_SW) : 1.f;
+            constexpr float inv_out = F16 ? 1.f / F16_SA : 1.f;
             const float l0 = __uint_as_float(rr[0]) * inv_out + S.b_out[0], l1 = __uint_as_float(rr[1]) * inv_out + S.b_out[1],
                         l2 = __uint_as_float(rr[2]) * inv_out + S.b_out[2];
             if (hq == 0 && live && P.logits) {
@@ -1327,7 +1330,7 @@ struct PackSeg { const float* src; int ld; int k0; int n_valid; int n_rows; uint
 
 // one thread per 16-byte chunk (8 elements) of a tile; image order inside a segment: kb0.hi, kb0.lo, kb1.hi, ...
 // `f16`: fp16 hi/lo instead of bf16 hi/lo.
-__global__ void pack_tc_kernel(uint8_t* __restrict__ img, PackSeg ps, int f16) {
+__global__ void pack_tc_kernel(uint8_t* __restrict__ img, PackSeg ps, int f16, float scale) {
   const int tile_bytes = ps.n_rows * 128;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int chunks_per_tile = ps.n_rows * 8;
@@ -1340,7 +1343,7 @@ __global__ void pack_tc_kernel(uint8_t* __restrict__ img, PackSeg ps, int f16) {
   for (int e = 0; e < 8; ++e) {
     float w = n < ps.n_valid ? ps.src[(int64_t)n * ps.ld + ps.k0 + kb * KBLK + j * 8 + e] : 0.f;
     if (f16) {
-      w *= F16_SW;
+      w *= scale;
       __half hi = __float2half_rn(w);
       __half v = part == 0 ? hi : __float2half_rn(w - __half2float(hi));
       out[e] = *reinterpret_cast<uint16_t*>(&v);
@@ -1490,8 +1493,10 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   const Plan pl = make_plan(w, H1);
   TcParams P{};
   const bool f16 = precision == DGDM_PREC_FP16 || precision == DGDM_PREC_FP16X3;
-  // the image buffer holds the bf16 image followed by the fp16 image (dgdm_dyn_pack_tc writes both)
-  P.img = (const uint8_t*)w->tc_image + (f16 ? pl.bytes : 0);
+  // the image buffer holds three images (dgdm_dyn_pack_tc): bf16 hi+lo, fp16 hi+lo scaled by F16_SW (fp16x3), and the
+  // unscaled fp16 image of the single-pass fp16 mode
+  const bool x3_mode = precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_FP16X3;
+  P.img = (const uint8_t*)w->tc_image + (f16 ? (x3_mode ? pl.bytes : 2 * pl.bytes) : 0);
   P.gscale = f16 ? F16_GS : 1.f;
   P.U = U; P.Cst = Cst; P.Vt = V;
   for (int i = 0; i < 7; ++i) P.bias[i] = w->bl[i];
@@ -1545,7 +1550,7 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   timing_lock.unlock();
   if (backward) {
     reduce_slots_kernel<<<(unsigned)((n_pairs * H1 + 255) / 256), 256, 0, s>>>(dUp, part, n_pairs, G, H1,
-                                                                               f16 ? 1.f / (F16_GS * F16_SW) : 1.f);
+                                                                               f16 ? 1.f / (F16_GS * (P.x3 ? F16_SW : 1.f)) : 1.f);
   } else {
     reduce_score_slots_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(score_sum, score_part, n_pairs, G);
   }
@@ -1608,7 +1613,7 @@ extern "C" int dgdm_trunk_timing_read_split(double* ms, int64_t* launches, int64
 
 extern "C" size_t dgdm_dyn_tc_image_bytes(int32_t H1) {
   if (H1 != 256 && H1 != 512) return 0;
-  return 2 * dgdm::make_plan(nullptr, H1).bytes;          // bf16 image + fp16 image
+  return 3 * dgdm::make_plan(nullptr, H1).bytes;          // bf16 image + fp16 x3 image + fp16 single-pass image
 }
 
 extern "C" int dgdm_dyn_pack_tc(const dgdm_dyn_weights* w, void* tc_image, void* stream) {
@@ -1617,11 +1622,11 @@ extern "C" int dgdm_dyn_pack_tc(const dgdm_dyn_weights* w, void* tc_image, void*
   DGDM_CHECK_ARG(w->H1 == 256 || w->H1 == 512, "dgdm_dyn_pack_tc: H1=%d unsupported", w->H1);
   DGDM_CHECK_ARG(((uintptr_t)tc_image) % 128 == 0, "dgdm_dyn_pack_tc: image must be 128-byte aligned");
   Plan pl = make_plan(w, w->H1);
-  for (int f16 = 0; f16 < 2; ++f16) {
+  for (int im = 0; im < 3; ++im) {             // 0: bf16, 1: fp16 x F16_SW (hi + lo), 2: fp16 unscaled (single pass)
     for (int i = 0; i < pl.n_seg; ++i) {
       const int chunks = 8 * pl.pack[i].n_rows * 8;
-      pack_tc_kernel<<<(chunks + 255) / 256, 256, 0, (cudaStream_t)stream>>>((uint8_t*)tc_image + (size_t)f16 * pl.bytes,
-                                                                            pl.pack[i], f16);
+      pack_tc_kernel<<<(chunks + 255) / 256, 256, 0, (cudaStream_t)stream>>>((uint8_t*)tc_image + (size_t)im * pl.bytes,
+                                                                            pl.pack[i], im > 0, im == 1 ? F16_SW : 1.f);
       DGDM_LAUNCH_CHECK();
     }
   }
