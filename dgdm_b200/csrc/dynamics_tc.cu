@@ -100,6 +100,14 @@ struct TcParams {
   float gscale;         // scale of the backward seed (1, or F16_GS in the fp16 modes)
   int alt;              // 1: an odd number of region swaps per tile -> alternate the start region tile by tile
   Seg seg[MAX_SEG];
+  // acc_mode (backward, G >= 128, one-tile kernel): a CTA owns a CONTIGUOUS range of tiles and adds a pair's per-tile
+  // column sums up itself, in ascending tile order (the association of the old per-(pair, tile) slot buffer + reduce
+  // kernel, bit for bit), writing dUp directly; only pairs cut by a CTA boundary go through `prefix` / `cont`.
+  int acc_mode, max_cont;
+  float inv_gscale;
+  float* dUp;           // [n_pairs][H1]
+  float* prefix;        // [grid][H1]            sum over the tiles of the CTA's last pair when it continues in the next CTA
+  float* cont;          // [grid][max_cont][H1]  per-tile sums of the CTA's leading tiles that continue an earlier CTA's pair
   // two-tile kernel (tc_trunk2_kernel): ReLU sign bits live in global scratch, work order lists for the two roles
   uint16_t* mask_scratch;
   int n_e, n_m;
@@ -368,7 +376,19 @@ struct Smem {
   float red_s[4];
   float lg[4][TILE_M][3];      // partial logits of the four 16-feature-group warps of a row
   uint16_t mask[2 * MASK_WORDS][TILE_M];      // ReLU sign bits, one halfword per (16-feature group, row)
+  float acc[512];               // acc_mode: running column sums of the pair that spans the current tiles
 };
+
+// acc_mode tile ownership: CTA b owns tiles [tile0, tile0 + count): the first n_tiles % grid CTAs one tile more
+__host__ __device__ inline void cta_tiles(int n_tiles, int grid, int b, int& tile0, int& count) {
+  const int q = n_tiles / grid, r = n_tiles % grid;
+  tile0 = b * q + (b < r ? b : r);
+  count = q + (b < r ? 1 : 0);
+}
+__host__ __device__ inline int tile_owner(int n_tiles, int grid, int tile) {
+  const int q = n_tiles / grid, r = n_tiles % grid;
+  return tile < r * (q + 1) ? tile / (q + 1) : r + (tile - r * (q + 1)) / q;
+}
 
 template <bool X3, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_constant__ TcParams P) {
@@ -407,7 +427,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
   // which starved the tensor pipe between weight tiles).
   if (tmem != 0u) { if (tid == 0 && P.err) atomicExch(P.err, 9); __trap(); }
 
-  const int tiles_mine = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  int tile0 = (int)blockIdx.x, tiles_mine = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  int tile_step = (int)gridDim.x;
+  if (P.acc_mode) { cta_tiles(P.n_tiles, (int)gridDim.x, (int)blockIdx.x, tile0, tiles_mine); tile_step = 1; }
   const int tiles_per_seg = X3 ? 8 : 4;       // weight tiles per segment: 4 k-blocks x (hi [, lo])
 
   if (warp == NEPI) {
@@ -494,7 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
     auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); };
 
     for (int t = 0; t < tiles_mine; ++t) {
-      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int tile = tile0 + t * tile_step;
       // Row -> (pair, pose row) with ONE 64-bit division per tile; everything per row is 32-bit (this code sits on the
       // tile-to-tile critical path: the timeline showed ~1900 cycles of index arithmetic here with 64-bit divisions).
       const int64_t base = (int64_t)tile * TILE_M;
@@ -832,7 +854,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (tid < 256) {
               const float s = (S.red[0][tid] + S.red[1][tid]) + (S.red[2][tid] + S.red[3][tid]);
-              P.part[(ps + tile) * P.H1 + sgm.half * 256 + tid] = s;
+              const int col = sgm.half * 256 + tid;
+              if (!P.acc_mode) {
+                P.part[(ps + tile) * P.H1 + col] = s;
+              } else {
+                const int64_t ta = (ps * P.G) / TILE_M, tb = ((ps + 1) * P.G - 1) / TILE_M;    // tiles of pair ps
+                if (ta < tile0) {                     // the pair started in an earlier CTA: hand the tile's sum to the fix-up
+                  P.cont[((int64_t)blockIdx.x * P.max_cont + (tile - tile0)) * P.H1 + col] = s;
+                } else {
+                  const float a = tile == ta ? s : S.acc[col] + s;       // ((s_ta + s_ta+1) + ...) : ascending tiles
+                  if (tile == tb) P.dUp[ps * P.H1 + col] = a * P.inv_gscale;
+                  else if (t == tiles_mine - 1) P.prefix[(int64_t)blockIdx.x * P.H1 + col] = a;
+                  S.acc[col] = a;
+                }
+              }
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
           }
@@ -1314,6 +1349,30 @@ __global__ void reduce_slots_kernel(float* __restrict__ dUp, const float* __rest
   for (int64_t t = t0; t <= t1; ++t) s += part[(p + t) * H1 + c];
   dUp[idx] = s * inv_gscale;          // exact: the scale is a power of two
 }
+// acc_mode tail: a pair cut by a CTA boundary = the starting CTA's prefix + the following tiles' sums, ascending.
+__global__ void fixup_pairs_kernel(float* __restrict__ dUp, const float* __restrict__ prefix, const float* __restrict__ cont,
+                                   int n_tiles, int grid, int G, int H1, int max_cont, int64_t n_rows, float inv_gscale) {
+  const int b = blockIdx.x;
+  int tile0, count;
+  cta_tiles(n_tiles, grid, b, tile0, count);
+  if (count == 0) return;
+  const int last_tile = tile0 + count - 1;
+  int64_t last_row = (int64_t)last_tile * TILE_M + TILE_M - 1;
+  if (last_row >= n_rows) last_row = n_rows - 1;
+  const int64_t p = last_row / G;
+  const int64_t ta = (p * G) / TILE_M, tb = ((p + 1) * G - 1) / TILE_M;
+  if (tb <= last_tile || ta < tile0) return;       // completed inside the CTA / started in an earlier one (its block does it)
+  for (int c = threadIdx.x; c < H1; c += blockDim.x) {
+    float s = prefix[(int64_t)b * H1 + c];
+    for (int64_t tile = last_tile + 1; tile <= tb; ++tile) {
+      const int o = tile_owner(n_tiles, grid, (int)tile);
+      int o0, oc;
+      cta_tiles(n_tiles, grid, o, o0, oc);
+      s += cont[((int64_t)o * max_cont + (tile - o0)) * H1 + c];
+    }
+    dUp[p * H1 + c] = s * inv_gscale;
+  }
+}
 __global__ void reduce_score_slots_kernel(float* __restrict__ out, const float* __restrict__ part, int64_t n_pairs, int G) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
@@ -1451,11 +1510,21 @@ Timing g_timing;
 
 }  // namespace
 
+// DGDM_TRUNK_SLOTS=1 keeps the round-1 reduction (one H1-wide slot per (pair, tile) + reduce_slots_kernel) for A/B tests
+static bool use_slots() {
+  static const bool on = [] { const char* e = getenv("DGDM_TRUNK_SLOTS"); return e && e[0] == '1'; }();
+  return on;
+}
+constexpr int MAX_GRID = 160;                  // acc_mode buffers are sized for this many CTAs
+static bool acc_mode_for(int G) { return G >= TILE_M && !use_slots() && !use_trunk2(); }
+static int max_cont_for(int G) { return G / TILE_M + 2; }     // tiles a pair can spill into later CTAs (bounded per CTA below)
+
 size_t tc_trunk_workspace_bytes(int H1, int64_t n_pairs, int G) {
   int64_t n_tiles = (n_pairs * G + TILE_M - 1) / TILE_M;
   int64_t slots = n_pairs + n_tiles;
-  return align_up((size_t)slots * H1 * sizeof(float), 256) + align_up((size_t)slots * sizeof(float), 256) + 256 +
-         align_up(MASK_SCRATCH_BYTES, 256);
+  const size_t sums = acc_mode_for(G) ? align_up((size_t)MAX_GRID * (1 + max_cont_for(G)) * H1 * sizeof(float), 256)
+                                      : align_up((size_t)slots * H1 * sizeof(float), 256);
+  return sums + align_up((size_t)slots * sizeof(float), 256) + 512 + align_up(MASK_SCRATCH_BYTES, 256);
 }
 
 int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const float* V, int n_designs, int n_obj,
@@ -1466,11 +1535,19 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   const int64_t n_rows = n_pairs * G;
   const int64_t n_tiles = (n_rows + TILE_M - 1) / TILE_M;
   DGDM_CHECK_ARG(n_tiles < (1ll << 30), "tc_trunk: too many tiles");
+  const bool acc_mode = acc_mode_for(G) && backward;
+  const int max_cont = max_cont_for(G);
   Arena ar(ws, ws_bytes);
-  float* part = ar.take<float>((size_t)(n_pairs + n_tiles) * H1);
   float* score_part = ar.take<float>((size_t)(n_pairs + n_tiles));
   int* err = ar.take<int>(1);
   uint16_t* mask_scratch = ar.take<uint16_t>(MASK_SCRATCH_BYTES / sizeof(uint16_t));
+  float *part = nullptr, *prefix = nullptr, *cont = nullptr;
+  if (acc_mode) {
+    prefix = ar.take<float>((size_t)MAX_GRID * H1);
+    cont = ar.take<float>((size_t)MAX_GRID * max_cont * H1);
+  } else if (backward) {
+    part = ar.take<float>((size_t)(n_pairs + n_tiles) * H1);
+  }
   if (!ar.ok) { set_error("tc_trunk: workspace too small"); return DGDM_EWORKSPACE; }
 
   // per-device one-time setup (one process normally drives one GPU, but do not assume it)
@@ -1521,10 +1598,13 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   const bool two_tile = !P.x3 && use_trunk2();
   P.mask_scratch = mask_scratch;
   if (two_tile) tc2_schedule(P);
+  P.acc_mode = acc_mode; P.max_cont = max_cont; P.dUp = dUp; P.prefix = prefix; P.cont = cont;
+  P.inv_gscale = f16 ? 1.f / (F16_GS * (P.x3 ? F16_SW : 1.f)) : 1.f;
 
   DGDM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
   int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   if (two_tile && grid > MAX_CTAS2) grid = MAX_CTAS2;
+  if (acc_mode && grid > MAX_GRID) grid = MAX_GRID;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   std::unique_lock<std::mutex> timing_lock(g_timing.mu);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -1548,9 +1628,10 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   DGDM_LAUNCH_CHECK();
   if (e1) DGDM_CUDA(cudaEventRecord(e1, s));
   timing_lock.unlock();
-  if (backward) {
-    reduce_slots_kernel<<<(unsigned)((n_pairs * H1 + 255) / 256), 256, 0, s>>>(dUp, part, n_pairs, G, H1,
-                                                                               f16 ? 1.f / (F16_GS * (P.x3 ? F16_SW : 1.f)) : 1.f);
+  if (acc_mode) {
+    fixup_pairs_kernel<<<grid, 256, 0, s>>>(dUp, prefix, cont, (int)n_tiles, grid, G, H1, max_cont, n_rows, P.inv_gscale);
+  } else if (backward) {
+    reduce_slots_kernel<<<(unsigned)((n_pairs * H1 + 255) / 256), 256, 0, s>>>(dUp, part, n_pairs, G, H1, P.inv_gscale);
   } else {
     reduce_score_slots_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(score_sum, score_part, n_pairs, G);
   }

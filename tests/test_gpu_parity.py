@@ -596,31 +596,39 @@ sys.path[:0] = [sys.argv[1], sys.argv[1] + "/tests", sys.argv[1] + "/oracle"]
 from dgdm_b200 import synthetic as syn
 from test_gpu_parity import make2d, make3d
 out = {}
-for prec in ("bf16", "fp16"):
-    dm = make2d(prec, syn.objects_2d(2), 36, 5)
+for prec in ("bf16", "fp16", "fp32"):
+    dm = make2d(prec, syn.objects_2d(2), 36, 5)                       # 2 x 40 x 900 rows = 563 tiles: pairs span CTAs
     x = syn.initial_noise(40, 14)[..., 0].cuda().repeat(2, 1).contiguous()
     out["2d_" + prec] = dm.guidance(x, 6, dm._obj_dev, 1, "rotate").cpu()
     out["2d_score_" + prec] = dm.score(x, dm._obj_dev, 1, "rotate_clockwise").cpu()
-    dm3 = make3d(prec, syn.objects_3d(2), syn.fps_starts(2), 9, 3)
+    dm3 = make3d(prec, syn.objects_3d(2), syn.fps_starts(2), 9, 3)    # G = 81 < 128: several pairs per tile
     x3 = syn.initial_noise(24, 42)[..., 0].cuda().repeat(2, 1).contiguous()
     out["3d_" + prec] = dm3.guidance(x3, 3, dm3._obj_dev, 1, "rotate_clockwise").cpu()
+    dm3b = make3d(prec, syn.objects_3d(2), syn.fps_starts(2), 15, 3)  # G = 135: tiles straddle pairs, 2 N-halves
+    out["3d_g135_" + prec] = dm3b.guidance(x3, 3, dm3b._obj_dev, 1, "rotate").cpu()
+    dmm = make2d(prec, syn.objects_2d(3), 36, 5)                      # multi-object fold: 3 objects per design
+    xm = syn.initial_noise(8, 14)[..., 0].cuda().contiguous()
+    out["2d_multi_" + prec] = dmm.guidance(xm, 9, dmm._obj_dev, 3, "rotate_clockwise").cpu()
 torch.save(out, sys.argv[2])
 """
 
 
-def test_two_tile_kernel_opt_in_is_bit_identical(tmp_path):
-    """DGDM_TRUNK2=1 routes the single-pass modes through tc_trunk2_kernel (two tiles in flight, SS-mode operands).  Same
-    operands, same K order, same reduction order: its gradients and scores equal the default kernel's bit for bit."""
+def test_kernel_variants_are_bit_identical(tmp_path):
+    """Three builds of the same arithmetic must agree bit for bit in gradients and scores:
+    the default path (a CTA owns a contiguous tile range and adds a pair's per-tile sums up itself, cut pairs fixed up);
+    DGDM_TRUNK_SLOTS=1, the round-1 reduction (one slot per (pair, tile) + reduce_slots_kernel): same ascending-tile order;
+    DGDM_TRUNK2=1, the two-tile SS-mode kernel for the single-pass modes: same operands, same K order, same reduction."""
     import os
     import subprocess
     import sys
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for flag in ("0", "1"):
-        path = str(tmp_path / f"trunk2_{flag}.pt")
+    for name, env in (("default", {}), ("slots", {"DGDM_TRUNK_SLOTS": "1"}), ("two_tile", {"DGDM_TRUNK2": "1"})):
+        path = str(tmp_path / f"variant_{name}.pt")
         r = subprocess.run([sys.executable, "-c", _TRUNK2_SCRIPT, repo, path], capture_output=True, text=True, timeout=600,
-                           env=dict(os.environ, DGDM_TRUNK2=flag))
-        assert r.returncode == 0, r.stderr[-3000:]
-        res[flag] = torch.load(path)
-    for k in res["0"]:
-        assert torch.equal(res["0"][k], res["1"][k]), (k, float((res["0"][k] - res["1"][k]).abs().max()))
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, (name, r.stderr[-3000:])
+        res[name] = torch.load(path)
+    for name in ("slots", "two_tile"):
+        for k in res["default"]:
+            assert torch.equal(res["default"][k], res[name][k]), (name, k, float((res["default"][k] - res[name][k]).abs().max()))
