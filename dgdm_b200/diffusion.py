@@ -512,9 +512,10 @@ class Diffusion:
         n_obj = self._obj_dev.shape[0]
         B, P = batch_size, self.num_points
         x0 = self._check_noise(noise, B)
-        # Bound the per-launch working set: the guidance kernel keeps one H1-wide partial sum per (pair, tile) in its
-        # workspace (~20 KB per design at G = 1125), so a 1024-object x 512-candidate sweep on one GPU would ask for
-        # 10 GB.  Objects are independent (diffusion.py:561-570), so chunks of objects give identical results.
+        # Bound the per-launch working set (U / dU / encoder intermediates: ~10 KB per design; with DGDM_TRUNK_SLOTS=1
+        # also one H1-wide partial sum per (pair, tile), ~20 KB per design at G = 1125): a 1024-object x 512-candidate
+        # sweep on one GPU runs as four launches per step.  Objects are independent (diffusion.py:561-570), so chunks of
+        # objects give identical results (test_object_chunking_is_invisible).
         per_launch = max(1, self.max_designs_per_launch // B)
         if n_obj > per_launch and opt_obj != "convergence" and trace is None:
             parts = [self._guided_sample_objects(self._obj_dev[o:o + per_launch], x0, opt_obj, ori_range, None, top_k, None)
