@@ -104,6 +104,7 @@ struct TcParams {
   // column sums up itself, in ascending tile order (the association of the old per-(pair, tile) slot buffer + reduce
   // kernel, bit for bit), writing dUp directly; only pairs cut by a CTA boundary go through `prefix` / `cont`.
   int acc_mode, max_cont;
+  int merge_ab;         // single-pass modes: the A k-block's hand-over arrives on the weight tile's `full` barrier (one wait)
   float inv_gscale;
   float* dUp;           // [n_pairs][H1]
   float* prefix;        // [grid][H1]            sum over the tiles of the CTA's last pair when it continues in the next CTA
@@ -405,7 +406,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    // merge_ab (single-pass modes): ONE barrier per weight tile covers both operands -- the weight bytes (producer's
+    // arrive.expect_tx) and the A k-block (one arrive per epilogue warp) -- so the issuing thread, which sets the pace
+    // between weight tiles (scripts/microbench/mma_2cta.cu), does one wait per four MMAs instead of two.  The fp32-grade
+    // modes keep the a_ready barriers (a k-block there is two weight tiles, and they run at the power cap anyway).
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&S.full[s], P.merge_ab ? 1 + NEPI : 1); mbar_init(&S.empty[s], 1); }
     for (int k = 0; k < 4; ++k) mbar_init(&S.a_ready[k], NEPI);
     mbar_init(&S.d_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           for (int j = 0; j < tiles_per_seg; ++j) {
             const int kb = X3 ? (j >> 1) : j, part = X3 ? (j & 1) : 0;
             TR(sg * 64 + j * 4 + 0);
-            if (part == 0) mbar_wait(&S.a_ready[kb], a_phase, P.err, 2);
+            if (part == 0 && !(!X3 && P.merge_ab)) mbar_wait(&S.a_ready[kb], a_phase, P.err, 2);
             TR(sg * 64 + j * 4 + 1);
             mbar_wait(&S.full[stage], phase, P.err, 3);
             tc_fence_after();
@@ -513,6 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int l1_hw = P.H1 / 16;                  // halfwords of layer-1 sign bits per row
     uint32_t d_phase = 0;
+    [[maybe_unused]] uint32_t pos_stage = 0;     // merge_ab: ring stage of weight tile 0 of the segment whose operand comes next
     auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); };
 
     for (int t = 0; t < tiles_mine; ++t) {
@@ -541,12 +547,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 
       // hand k-block kb of the A operand over to the MMA issuer
       [[maybe_unused]] int tr_sg = 0;
+      // (merge_ab: the k-block goes with weight tile kb of the segment it feeds, i.e. ring stage pos_stage + kb; every
+      // segment's operand is produced exactly once and takes four weight tiles, so pos_stage tracks the issuer's counter.
+      // Phase safety: position p - NSTAGE of that stage lies in the layer whose accumulator this epilogue is reading, so
+      // its phase has completed.)
       auto signal_kb = [&](int kb) {
         tmem_wait_st();
         TRE(kb, 9);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.a_ready[kb]);
+        if (!X3 && P.merge_ab) {
+          if (lane == 0) { uint32_t st = pos_stage + (uint32_t)kb; if (st >= NSTAGE) st -= NSTAGE; mbar_arrive(&S.full[st]); }
+          if (kb == 3) { pos_stage += 4; if (pos_stage >= NSTAGE) pos_stage -= NSTAGE; }
+        } else if (lane == 0) {
+          mbar_arrive(&S.a_ready[kb]);
+        }
         TRE(kb, 10);
       };
       // store 16 features (k-block kb, group hq) of this row as bf16 hi [+ lo] into region `reg`
@@ -1598,6 +1613,10 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   const bool two_tile = !P.x3 && use_trunk2();
   P.mask_scratch = mask_scratch;
   if (two_tile) tc2_schedule(P);
+  {
+    static const bool merge = [] { const char* e = getenv("DGDM_TRUNK_MERGE"); return !(e && e[0] == '0'); }();
+    P.merge_ab = (!P.x3 && merge) ? 1 : 0;
+  }
   P.acc_mode = acc_mode; P.max_cont = max_cont; P.dUp = dUp; P.prefix = prefix; P.cont = cont;
   P.inv_gscale = f16 ? 1.f / (F16_GS * (P.x3 ? F16_SW : 1.f)) : 1.f;
 
