@@ -165,9 +165,12 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
             bar_wait(&S.w_full[sw], pw, P.err, 25);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t wb = s32(wring + (size_t)sw * w_tile);
+            // (one add per descriptor and K step: + 32 bytes = + 2 in the 14-bit address field; the issuing thread sets the
+            // pace of N = 128 MMAs, scripts/microbench/mma_2cta.cu)
+            const uint64_t wd0 = sw128_desc(wb);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t wd = sw128_desc(wb + ks * 32);
+              const uint64_t wd = wd0 + (uint64_t)(2 * ks);
               mma_ss(d, ad_hi + (uint64_t)(ks * 2 * PLANE_B >> 4), wd, idesc, accum);
               accum = 1;
               if (P.x3) mma_ss(d, ad_lo + (uint64_t)(ks * 2 * PLANE_B >> 4), wd, idesc, 1);
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               wb = s32(wring + (size_t)sw * w_tile);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) mma_ss(d, ad_hi + (uint64_t)(ks * 2 * PLANE_B >> 4), sw128_desc(wb + ks * 32), idesc, 1);
+              for (int ks = 0; ks < 4; ++ks) mma_ss(d, ad_hi + (uint64_t)(ks * 2 * PLANE_B >> 4), sw128_desc(wb) + (uint64_t)(2 * ks), idesc, 1);
               commit(&S.w_empty[sw]);
               if (++sw == (uint32_t)P.n_w) { sw = 0; pw ^= 1; }
             }
