@@ -26,7 +26,7 @@ Keys beside the driver's contract:
                of those launches inside the timed region; the forward-only scoring launches are reported separately
                (`scoring`).  In the fp32-grade modes every product is 3 MMAs, so the peak is the measured sustained
                bf16 peak / 3 (`peak_basis`).
-  cpu_baseline the REFERENCE's own `Diffusion.guided_sample` (unmodified files under oracle/_ref, oracle/ref_arm.py)
+  cpu_baseline the REFERENCE's own `Diffusion.guided_sample` (its modules byte-compiled under oracle/_ref, oracle/ref_arm.py)
                on a bounded slice of the same workload on this box's host cores; `port` = the oracle restatement
                (hoist-free but without the reference's Python tiling) on the same slice; `c1_as_is` = the reference on
                BASELINE.json configs[0] (1 object x 16 candidates x 360 x 5x5 = 9000 pose rows), one pass.
@@ -193,7 +193,7 @@ class CpuArm:
         self._run()
 
     def describe(self):
-        what = ("the reference's own Diffusion.guided_sample (generator/diffusion.py:541-576, unmodified files from "
+        what = ("the reference's own Diffusion.guided_sample (generator/diffusion.py:541-576, its unmodified modules, byte-compiled under "
                 "oracle/_ref: Python tiling, autograd backward, per-row encoders; DDIM stub for diffusers, MuJoCo call "
                 "replaced by a recorder, no predicted-score pass)") if self.kind == "reference" else \
                ("CPU oracle port (oracle/dgdm_oracle.py: reference algorithm with repeat-based tiling and PointNet++ "

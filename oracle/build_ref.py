@@ -1,13 +1,15 @@
 #!/usr/bin/env python
-"""Recipe for oracle/_ref/: the reference's OWN sampler sources, for bench.py's ``--impl reference`` arm.
+"""Recipe for oracle/_ref/: the reference's OWN sampler, compiled, for bench.py's ``--impl reference`` arm.
 
-The reference is pure Python, so "building" it is copying the seven files of the path that import with torch + numpy
-alone, from where they lie under /root/reference, into oracle/_ref/reference/ (git-ignored build output: it travels
-to the GPU box with the snapshot like a built .so, and never enters the history).  Nothing is modified.  Run by
-``__graft_entry__.build()`` whenever /root/reference is present (the authoring container); on the GPU box the copies
-that travelled are used.  TEST INFRASTRUCTURE: only bench.py's reference arm (through oracle/ref_arm.py) reads it.
+The reference is pure Python, so "building" it is byte-compiling the seven files of the path that import with torch +
+numpy alone, from the sources where they lie under /root/reference, into sourceless ``.pyc`` modules under
+oracle/_ref/reference/ (git-ignored build output: it travels to the GPU box with the snapshot like a built .so, and never
+enters the history; no reference source is copied into this repository).  Run by ``__graft_entry__.build()`` whenever
+/root/reference is present (the authoring container); on the GPU box the modules that travelled are used (same image,
+same CPython).  TEST INFRASTRUCTURE: only bench.py's reference arm (through oracle/ref_arm.py) imports it.
 """
 import os
+import py_compile
 import shutil
 import sys
 
@@ -24,15 +26,17 @@ def build(verbose: bool = True) -> bool:
         if verbose:
             print(f"oracle/_ref: {REF} not present; keeping whatever travelled with the tree")
         return os.path.isdir(DST)
+    if os.path.isdir(DST):
+        shutil.rmtree(DST)                        # never leave stale modules (or sources of an older recipe) behind
     for rel in FILES:
-        src, dst = os.path.join(REF, rel), os.path.join(DST, rel)
+        src, dst = os.path.join(REF, rel), os.path.join(DST, rel + "c")          # module.py -> module.pyc (sourceless import)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
-        shutil.copyfile(src, dst)
+        py_compile.compile(src, cfile=dst, dfile=rel, doraise=True, optimize=0)
     with open(os.path.join(DST, "PROVENANCE.txt"), "w") as f:
-        f.write("Unmodified copies of real-stanford/dgdm files made by oracle/build_ref.py from " + REF + ":\n"
-                + "\n".join(FILES) + "\n")
+        f.write("CPython %d.%d bytecode of real-stanford/dgdm files, compiled unmodified by oracle/build_ref.py from %s:\n"
+                % (sys.version_info[0], sys.version_info[1], REF) + "\n".join(FILES) + "\n")
     if verbose:
-        print(f"oracle/_ref: {len(FILES)} reference files -> {DST}")
+        print(f"oracle/_ref: {len(FILES)} reference modules byte-compiled -> {DST}")
     return True
 
 

@@ -1,5 +1,5 @@
 """bench.py's reference arm: the reference's own ``Diffusion.guided_sample`` (generator/diffusion.py:541-576), run
-unmodified from the copies under oracle/_ref/reference (oracle/build_ref.py) on the host cores.
+unmodified from the byte-compiled modules under oracle/_ref/reference (oracle/build_ref.py) on the host cores.
 
 What runs is the reference's method itself -- its objects loop, its ``cond_fn`` with the Python list-comprehension
 tiling (diffusion.py:478-486, a third of its time), its ConditionalUnet1D, its DataParallel wrapper -- with random-init
@@ -28,7 +28,7 @@ _RECORDED = []
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REF_ROOT, "generator", "diffusion.py"))
+    return os.path.exists(os.path.join(REF_ROOT, "generator", "diffusion.pyc"))
 
 
 def _record(sample, object_ids, save_dir, **kwargs):
