@@ -2,8 +2,8 @@
 """Recipe for oracle/_ref/: the reference's OWN sampler, compiled, for bench.py's ``--impl reference`` arm.
 
 The reference is pure Python, so "building" it is byte-compiling the seven files of the path that import with torch +
-numpy alone, from the sources where they lie under /root/reference, into sourceless ``.pyc`` modules under
-oracle/_ref/reference/ (git-ignored build output: it travels to the GPU box with the snapshot like a built .so, and never
+numpy alone, from the sources where they lie under /root/reference, into CPython bytecode (``<module>.refbin``: a .pyc under a
+name the snapshot tools do not filter out; oracle/ref_arm.py has the importer) under oracle/_ref/reference/ (git-ignored build output: it travels to the GPU box with the snapshot like a built .so, and never
 enters the history; no reference source is copied into this repository).  Run by ``__graft_entry__.build()`` whenever
 /root/reference is present (the authoring container); on the GPU box the modules that travelled are used (same image,
 same CPython).  TEST INFRASTRUCTURE: only bench.py's reference arm (through oracle/ref_arm.py) imports it.
@@ -29,7 +29,7 @@ def build(verbose: bool = True) -> bool:
     if os.path.isdir(DST):
         shutil.rmtree(DST)                        # never leave stale modules (or sources of an older recipe) behind
     for rel in FILES:
-        src, dst = os.path.join(REF, rel), os.path.join(DST, rel + "c")          # module.py -> module.pyc (sourceless import)
+        src, dst = os.path.join(REF, rel), os.path.join(DST, rel[:-3] + ".refbin")   # module.py -> module.refbin (pyc bytes)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, dfile=rel, doraise=True, optimize=0)
     with open(os.path.join(DST, "PROVENANCE.txt"), "w") as f:

@@ -10,6 +10,9 @@ designs and returns no metrics -- the method then skips its logging for that obj
 continue``) and raises IndexError at its summary line (:611), which ``guided_sample`` below swallows.
 TEST INFRASTRUCTURE (see dgdm_oracle.py).
 """
+import importlib.abc
+import importlib.util
+import marshal
 import os
 import sys
 import tempfile
@@ -27,8 +30,33 @@ for p in (REPO, HERE):
 _RECORDED = []
 
 
+class _RefbinFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Imports ``<package dir>/<module>.refbin`` (the bytes of a .pyc written by oracle/build_ref.py) as ``module``."""
+
+    def find_spec(self, fullname, path, target=None):
+        name = fullname.rpartition(".")[2]
+        for entry in (path or [REF_ROOT]):
+            f = os.path.join(entry, name + ".refbin")
+            if os.path.isfile(f) and os.path.abspath(f).startswith(os.path.abspath(REF_ROOT)):
+                return importlib.util.spec_from_loader(fullname, self, origin=f)
+        return None
+
+    def exec_module(self, module):
+        with open(module.__spec__.origin, "rb") as fh:
+            data = fh.read()
+        if data[:4] != importlib.util.MAGIC_NUMBER:
+            raise ImportError(f"{module.__spec__.origin}: bytecode of another CPython (rebuild with oracle/build_ref.py)")
+        module.__file__ = module.__spec__.origin[:-len(".refbin")] + ".py"      # the reference modules read __file__
+        exec(marshal.loads(data[16:]), module.__dict__)
+
+
+def _install_finder():
+    if not any(isinstance(f, _RefbinFinder) for f in sys.meta_path):
+        sys.meta_path.append(_RefbinFinder())
+
+
 def available() -> bool:
-    return os.path.exists(os.path.join(REF_ROOT, "generator", "diffusion.pyc"))
+    return os.path.exists(os.path.join(REF_ROOT, "generator", "diffusion.refbin"))
 
 
 def _record(sample, object_ids, save_dir, **kwargs):
@@ -40,6 +68,7 @@ def build(mode: str, objects: torch.Tensor, grid_size: int, num_pos: int, sub_ba
     """The reference's Diffusion LightningModule around its real networks (eval mode, parameters frozen as
     generator/train.py:91-92 does)."""
     import ref_stubs
+    _install_finder()
     ref_stubs.install_stubs(REF_ROOT, sim_test_batch=_record, sim_test_batch_3d=_record)
     import warnings
     warnings.filterwarnings("ignore")

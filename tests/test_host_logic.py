@@ -289,7 +289,7 @@ def test_bench_reference_arm_prints_the_contract_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
-    have_ref = os.path.exists(os.path.join(repo, "oracle", "_ref", "reference", "generator", "diffusion.pyc"))
+    have_ref = os.path.exists(os.path.join(repo, "oracle", "_ref", "reference", "generator", "diffusion.refbin"))
     assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
     # other ranks of a torchrun launch exit 0 without work
     r = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
