@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[3] ("C4"): dynamics-network forward and forward+input-gradient throughput on explicit rows
 (the ProfileForward{2,3}DModel.forward signature: a distinct finger, pose, time and object per row, so nothing is
-hoisted), N = 1k .. 64k rows, both networks, fp32-grade and bf16.  Prints one JSON line per point.
+hoisted), N = 1k .. 64k rows, both networks, fp32-grade, fp16 and bf16.  Prints one JSON line per point.
 3D rows take pre-computed PointNet++ codes (one K5 call per distinct object), as the sampler does.
 
     python scripts/sweep_c4.py [--cpu]      # --cpu also times the oracle port on the host cores at N = 4096
@@ -36,7 +36,7 @@ def main():
         is3d = mode == "point_3d"
         n_obj = 16
         objs = syn.objects_3d(n_obj) if is3d else syn.objects_2d(n_obj)
-        for precision in ("fp32", "bf16"):
+        for precision in ("fp32", "fp16", "bf16"):
             dm = Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(15), 5, mode=mode, num_points=P,
                            classifier_model=syn.dynamics3d_state_dict(0) if is3d else syn.dynamics2d_state_dict(0),
                            grid_size=4, num_pos=1, object_vertices=objs, object_ids=list(range(n_obj)),
