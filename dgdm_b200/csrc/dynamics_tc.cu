@@ -65,9 +65,16 @@ constexpr int NEPI = 16;                       // epilogue warps: 4 per TMEM lan
 constexpr int NTHREADS = (NEPI + 2) * 32;      // + producer warp + MMA warp
 constexpr int MAX_SEG = 20;
 // two-tile single-pass kernel (tc_trunk2_kernel)
-constexpr int NS2 = 4;                         // operand ring: one stage per k-block of a segment = [weight tile 32 KB | A k-block 16 KB]
 constexpr int AKB_BYTES = 128 * 128;           // one A k-block: 128 rows x 128 B
-constexpr int STAGE2_BYTES = 256 * KBLK * 2 + AKB_BYTES;   // 48 KB (a multiple of 1024: both parts stay swizzle-aligned)
+// operand ring of the two-tile kernel: a stage = [weight part | A k-block 16 KB] of one k-block.  One CTA: the whole
+// 32 KB weight tile, 4 stages (= one segment).  CTA pair (cta_group::2, M = 256 over two SMs): each CTA stages its
+// 128 of the 256 weight rows (16 KB), so six 32 KB stages fit: one and a half segments of operands in flight.
+template <int NCTA> struct Ring2 {
+  static constexpr int NS = NCTA == 2 ? 6 : 4;
+  static constexpr int WPART = 256 * KBLK * 2 / NCTA;
+  static constexpr int STAGE = WPART + AKB_BYTES;          // a multiple of 1024: both parts stay swizzle-aligned
+};
+constexpr int NS2_MAX = 6;
 constexpr int MAX_ITEMS = 44;                  // work items per tile pair and role: bit 7 = tile slot, bits 0..6 = segment
 constexpr int IT_A1 = 0x7E;                    // item codes 0x7E / 0x7F: build the layer-1 operand, K-half 0 / 1
 constexpr int MAX_CTAS2 = 160;                 // mask scratch is sized for this many CTAs
@@ -175,6 +182,32 @@ __device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
+// CTA-pair forms (issued by the leader CTA only): M = 256 over the two SMs of the pair, each CTA supplies its 128 rows
+// of A and its half of the B rows from the same shared-memory offsets; the commit arrives on the barrier at the same
+// offset in BOTH CTAs
+__device__ __forceinline__ void tc_mma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  if ((threadIdx.x & 31) == 0)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+  if ((threadIdx.x & 31) == 0)
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -218,8 +251,8 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
 }
 // Instruction descriptor: D fp32, A/B bf16 (format 1) or fp16 (format 0), both K-major, M = 128, N = n.
 template <bool F16>
-__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (F16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n, int m = TILE_M) {
+  return (1u << 4) | (F16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ int pair_obj(int64_t p, int opd, int n_designs, int n_obj, const int32_t* pair_object) {
@@ -936,7 +969,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
 // producer refills the W part.
 // =============================================================================================
 struct Smem2 {
-  uint64_t full[NS2], empty[NS2], d_ready[2], d_free[2];
+  uint64_t full[NS2_MAX], empty[NS2_MAX], d_ready[2], d_free[2];
   uint32_t tmem_base, pad_;
   alignas(16) float bias[7][256];
   alignas(16) float w_out[3][256];
@@ -952,57 +985,72 @@ struct Smem2 {
 #define TR2(slot_) do { } while (0)
 #endif
 
-template <bool F16>
+template <bool F16, int NCTA>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_constant__ TcParams P) {
+  using R2 = Ring2<NCTA>;
+  constexpr int NS2 = R2::NS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  Smem2& S = *reinterpret_cast<Smem2*>(ring + NS2 * STAGE2_BYTES);
+  Smem2& S = *reinterpret_cast<Smem2*>(ring + NS2 * R2::STAGE);
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  uint32_t rank = 0;                              // CTA pair: 0 = leader (issues the MMAs), 1 = peer
+  if (NCTA == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
 
   if (tid == 0) {
-    for (int s = 0; s < NS2; ++s) { mbar_init(&S.full[s], NEPI + 1); mbar_init(&S.empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&S.d_ready[s], 1); mbar_init(&S.d_free[s], NEPI); }
+    // CTA pair: the leader's `full` / `d_free` barriers also take one arrival per phase from the peer's relay warp
+    const uint32_t extra = (NCTA == 2 && rank == 0) ? 1u : 0u;
+    for (int s = 0; s < NS2; ++s) { mbar_init(&S.full[s], NEPI + 1 + extra); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&S.d_ready[s], 1); mbar_init(&S.d_free[s], NEPI + extra); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 7 * 256; i += NTHREADS) S.bias[i / 256][i % 256] = P.bias[i / 256][i % 256] * (F16 ? F16_SA : 1.f);
   for (int i = tid; i < 3 * 256; i += NTHREADS) S.w_out[i / 256][i % 256] = P.w_out[i];
   if (tid < 3) S.b_out[tid] = P.b_out[tid];
   if (warp == NEPI + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) cluster_sync_all();               // both CTAs' barriers exist before anything remote touches them
   tc_fence_after();
   if (S.tmem_base != 0u) { if (tid == 0 && P.err) atomicExch(P.err, 9); __trap(); }   // literal TMEM addresses below
 
-  const int tiles_mine = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // both CTAs of a pair walk the same number of tile pairs (the leader's: it owns the lower block index); a CTA whose
+  // tile index runs past the end processes dead rows
+  const int tiles_mine = (P.n_tiles - ((int)blockIdx.x - (int)rank) + (int)gridDim.x - 1) / (int)gridDim.x;
   const int pairs_mine = (tiles_mine + 1) / 2;
 
   if (warp == NEPI) {
     // =============================== producer ===============================
     if (lane == 0) {
-      uint32_t phase = 0;
+      uint32_t stage = 0, phase = 0;
       for (int t = 0; t < pairs_mine; ++t) {
         const bool has1 = 2 * t + 1 < tiles_mine;
         for (int i = 0; i < P.n_m; ++i) {
           const uint32_t it = P.m_items[i];
           if ((it >> 7) && !has1) continue;
           const Seg sgm = P.seg[it & 0x7Fu];
-          const uint32_t tile_bytes = (uint32_t)sgm.n_rows * 128u;
+          const uint32_t tile_bytes = (uint32_t)sgm.n_rows * 128u, my_bytes = tile_bytes / NCTA;   // CTA pair: my half of the rows
           for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&S.empty[kb], phase ^ 1, P.err, 1);
-            mbar_arrive_expect_tx(&S.full[kb], tile_bytes);
+            mbar_wait(&S.empty[stage], phase ^ 1, P.err, 1);
+            mbar_arrive_expect_tx(&S.full[stage], my_bytes);
             // image order inside a segment: kb0.hi, kb0.lo, kb1.hi, ...; the single-pass modes read the hi parts
-            bulk_g2s(ring + kb * STAGE2_BYTES, P.img + sgm.img_off + (size_t)(kb * 2) * tile_bytes, tile_bytes, &S.full[kb]);
+            bulk_g2s(ring + stage * R2::STAGE, P.img + sgm.img_off + (size_t)(kb * 2) * tile_bytes + (size_t)rank * my_bytes, my_bytes,
+                     &S.full[stage]);
+            if (++stage == NS2) { stage = 0; phase ^= 1; }
           }
-          phase ^= 1;
         }
       }
     }
-  } else if (warp == NEPI + 1) {
+  } else if (warp == NEPI + 1 && rank == 0) {
     // =============================== MMA issuer (whole warp, uniform; lane 0 issues) ===============================
-    uint32_t phase = 0, df_ph = 0;
+    uint32_t stage = 0, phase = 0, df_ph = 0;
     for (int t = 0; t < pairs_mine; ++t) {
       const bool has1 = 2 * t + 1 < tiles_mine;
       for (int i = 0; i < P.n_m; ++i) {
@@ -1017,28 +1065,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
         }
         TR2(i * 16 + 1);
         const uint32_t d_base = slot * 256u;
-        const uint32_t idesc = make_idesc<F16>(sgm.n_rows);
+        const uint32_t idesc = make_idesc<F16>(sgm.n_rows, TILE_M * NCTA);
         uint32_t accum = sgm.accum;
-#pragma unroll
+#pragma unroll 1
         for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&S.full[kb], phase, P.err, 3);
+          mbar_wait(&S.full[stage], phase, P.err, 3);
           tc_fence_after();
           TR2(i * 16 + 3 + kb * 3);
           // descriptors of the four K = 16 steps: + 32 bytes = + 2 in the 14-bit address field (no carry: < 227 KB), so
           // one add per descriptor instead of a shift / mask / or chain on the uniform datapath before every MMA
-          const uint32_t b_addr = smem_u32(ring + kb * STAGE2_BYTES);
-          const uint64_t bd0 = make_b_desc(b_addr), ad0 = make_b_desc(b_addr + 256 * KBLK * 2);
+          const uint32_t b_addr = smem_u32(ring + stage * R2::STAGE);
+          const uint64_t bd0 = make_b_desc(b_addr), ad0 = make_b_desc(b_addr + R2::WPART);
 #pragma unroll
           for (int ks = 0; ks < KBLK / 16; ++ks) {
-            tc_mma_ss(d_base, ad0 + (uint64_t)(2 * ks), bd0 + (uint64_t)(2 * ks), idesc, accum);
+            if (NCTA == 2) tc_mma_ss2(d_base, ad0 + (uint64_t)(2 * ks), bd0 + (uint64_t)(2 * ks), idesc, accum);
+            else tc_mma_ss(d_base, ad0 + (uint64_t)(2 * ks), bd0 + (uint64_t)(2 * ks), idesc, accum);
             accum = 1;
           }
-          tc_commit(&S.empty[kb]);
+          if (NCTA == 2) tc_commit2(&S.empty[stage]); else tc_commit(&S.empty[stage]);
           TR2(i * 16 + 4 + kb * 3);
+          if (++stage == NS2) { stage = 0; phase ^= 1; }
         }
-        phase ^= 1;
-        if (sgm.kind != K_MID) tc_commit(&S.d_ready[slot]);
+        if (sgm.kind != K_MID) { if (NCTA == 2) tc_commit2(&S.d_ready[slot]); else tc_commit(&S.d_ready[slot]); }
         TR2(i * 16 + 14);
+      }
+    }
+  } else if (warp == NEPI + 1) {
+    // =============================== relay (peer CTA of a pair) ===============================
+    // forwards this CTA's "stage full" and "accumulator read" events to the leader's barriers, in the issuer's order
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, df_ph = 0, df_seen = 0;
+      for (int t = 0; t < pairs_mine; ++t) {
+        const bool has1 = 2 * t + 1 < tiles_mine;
+        for (int i = 0; i < P.n_m; ++i) {
+          const uint32_t it = P.m_items[i];
+          const uint32_t slot = it >> 7, sg = it & 0x7Fu;
+          if (slot && !has1) continue;
+          const Seg sgm = P.seg[sg];
+          if (!sgm.accum) {
+            if ((df_seen >> slot) & 1u) {           // (the first use of an accumulator waits for nobody, here and in the leader)
+              mbar_wait(&S.d_free[slot], (df_ph >> slot) & 1u, P.err, 7);
+              df_ph ^= 1u << slot;
+              mbar_arrive_remote(&S.d_free[slot], 0);
+            }
+            df_seen |= 1u << slot;
+          }
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&S.full[stage], phase, P.err, 8);
+            mbar_arrive_remote(&S.full[stage], 0);
+            if (++stage == NS2) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
   } else {
@@ -1047,19 +1124,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int l1_hw = P.H1 / 16;
-    uint32_t ekb = 0, eph = 0, dr_ph = 0;        // next stage to fill (= k-block index of the production), its phase
+    uint32_t est = 0, eph = 0, dr_ph = 0, ekb = 0, est0 = 0;   // next stage to fill + its phase; k-block within the item; item's first stage
     uint16_t* const mask_cta = P.mask_scratch + (size_t)blockIdx.x * 2 * (2 * MASK_WORDS) * TILE_M + row;
 
-    // this warp's 32 rows x 16 features of the next A k-block -> stage[ekb].A (canonical K-major SWIZZLE_128B);
-    // `write` = false: the operand is already there (3D, second N-half of the last GEMM): only hand the stage over again
+    // this warp's 32 rows x 16 features of the next A k-block -> stage[est].A (canonical K-major SWIZZLE_128B);
+    // `write` = false (one-CTA form only: 4 stages = one segment): the operand is already there (3D, second N-half of
+    // the last GEMM, same physical stages): only hand the stages over again
     [[maybe_unused]] int tr_i = 0, tr_t = 0, tr_kb = 0;
     auto put_kb = [&](const uint32_t (&hi)[8], bool write) {
-      mbar_wait(&S.empty[ekb], eph ^ 1u, P.err, 6);
+      mbar_wait(&S.empty[est], eph ^ 1u, P.err, 6);
 #ifdef DGDM_TRUNK_TRACE
       { const int t = tr_t; TR2(2048 + tr_i * 16 + 8 + (tr_kb & 3)); }
 #endif
+      if (ekb == 0) est0 = est;
       if (write) {
-        uint8_t* dst = ring + ekb * STAGE2_BYTES + 256 * KBLK * 2 + row * 128;
+        uint8_t* dst = ring + est * R2::STAGE + R2::WPART + row * 128;
         const int sw = row & 7;
         *reinterpret_cast<uint4*>(dst + (((2 * hq) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(dst + (((2 * hq + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -1068,18 +1147,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
       // cycles, four of them per item made the epilogue the slowest role.  Tried instead: st.async (STAS, needs a cluster
       // launch) with transaction-count completion and no fence: 6600 cycles per item; the fence from lane 0 only, per
       // k-block: no gain.
-      if (ekb == NS2 - 1) {
+      if (ekb == 3) {
         if (write) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
+          uint32_t st = est0;
 #pragma unroll
-          for (int k = 0; k < NS2; ++k) mbar_arrive(&S.full[k]);
+          for (int k = 0; k < 4; ++k) { mbar_arrive(&S.full[st]); if (++st == NS2) st = 0; }
         }
       }
 #ifdef DGDM_TRUNK_TRACE
       { const int t = tr_t; TR2(2048 + tr_i * 16 + 2 + (tr_kb & 3)); ++tr_kb; }
 #endif
-      if (++ekb == NS2) { ekb = 0; eph ^= 1u; }
+      ekb = (ekb + 1) & 3;
+      if (++est == NS2) { est = 0; eph ^= 1u; }
     };
 
     for (int t = 0; t < pairs_mine; ++t) {
@@ -1218,7 +1299,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
           const int64_t pr = live ? p_first + dq : -1;
           int64_t last_row = base + TILE_M - 1;
           if (last_row >= P.n_rows) last_row = P.n_rows - 1;
-          const int64_t p_last = p_first + (rem0 + (uint32_t)(last_row - base)) / Gu;
+          const int64_t p_last = base < P.n_rows ? p_first + (rem0 + (uint32_t)(last_row - base)) / Gu : p_first - 1;   // past the end: no pairs
           if (sgm.kind == K_OUT) {
             const float coef = (live && P.obj.row_coef) ? P.obj.row_coef[r_glob] : 1.f;
             const int mbase = l1_hw + 6 * 16;
@@ -1346,9 +1427,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) cluster_sync_all();               // the pair's MMAs touch both CTAs' TMEM and shared memory
   if (warp == NEPI + 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(0u) : "memory");
+    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(0u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(0u) : "memory");
   }
 }
 
@@ -1464,18 +1547,17 @@ Plan make_plan(const dgdm_dyn_weights* w, int H1) {
 }
 
 size_t smem_bytes() { return 1024 + (size_t)NSTAGE * WTILE_BYTES + sizeof(Smem); }
-size_t smem2_bytes() { return 1024 + (size_t)NS2 * STAGE2_BYTES + sizeof(Smem2); }
+template <int NCTA> size_t smem2_bytes() { return 1024 + (size_t)Ring2<NCTA>::NS * Ring2<NCTA>::STAGE + sizeof(Smem2); }
 constexpr size_t MASK_SCRATCH_BYTES = (size_t)MAX_CTAS2 * 2 * (2 * MASK_WORDS) * TILE_M * sizeof(uint16_t);
 
-// DGDM_TRUNK2=1 runs the single-pass modes on the two-tile kernel.  Off by default: it is parity-green but not faster
-// (0.71 vs 0.74 of roofline at C2) -- with the activations in shared memory the SS-mode MMAs read A (32 B/clk) and B
-// (64 B/clk) while the weight ring refills at 64 B/clk and the epilogue stores 32 B/clk: 192 B/clk against the
-// 128 B/clk shared memory delivers, so a layer of a tile takes ~3400 cycles there as well (timeline
-// profiles/trunk2_timeline_r02_bf16.txt).
-bool use_trunk2() {
-  static const bool on = [] { const char* e = getenv("DGDM_TRUNK2"); return e && e[0] == '1'; }();
-  return on;
+// DGDM_TRUNK2=1 runs the single-pass modes on the two-tile kernel, DGDM_TRUNK2=2 on its CTA-pair form (cta_group::2:
+// each CTA stages half of every weight tile, which makes room for a ring of one and a half segments).  Off by default:
+// see DESIGN.md 4.1 for the measurements.
+int trunk2_mode() {
+  static const int mode = [] { const char* e = getenv("DGDM_TRUNK2"); return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }();
+  return mode;
 }
+bool use_trunk2() { return trunk2_mode() != 0; }
 
 // Work lists of the two-tile kernel for one pair of tiles (slot 0 = X, slot 1 = Y).  The epilogue list is the
 // interleave E(X,sg), E(Y,sg); the MMA list is derived from it so that the issuer consumes the A ring in exactly the
@@ -1577,8 +1659,10 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
     DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     DGDM_CUDA(cudaFuncSetAttribute(tc_trunk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
-    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2_bytes()));
-    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2_bytes()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2_bytes<1>()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2_bytes<1>()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2_bytes<2>()));
+    DGDM_CUDA(cudaFuncSetAttribute(tc_trunk2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2_bytes<2>()));
     sm_counts[dev] = n;
   }
   const int sm_count = sm_counts[dev];
@@ -1638,8 +1722,22 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
     g_timing.pair_rows.push_back(n_rows);
     DGDM_CUDA(cudaEventRecord(e0, s));
   }
-  if (two_tile && f16) tc_trunk2_kernel<true><<<grid, NTHREADS, smem2_bytes(), s>>>(P);
-  else if (two_tile) tc_trunk2_kernel<false><<<grid, NTHREADS, smem2_bytes(), s>>>(P);
+  // CTA-pair form: not for the 3D backward launch (its last GEMM re-uses an operand in place, which needs the
+  // four-stage ring of the one-CTA form) and not for a single tile
+  const bool pair = two_tile && trunk2_mode() == 2 && !(H1 == 512 && backward) && grid >= 2;
+  if (pair) {
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem2_bytes<2>(); cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (f16) DGDM_CUDA(cudaLaunchKernelEx(&cfg, tc_trunk2_kernel<true, 2>, P));
+    else DGDM_CUDA(cudaLaunchKernelEx(&cfg, tc_trunk2_kernel<false, 2>, P));
+  }
+  else if (two_tile && f16) tc_trunk2_kernel<true, 1><<<grid, NTHREADS, smem2_bytes<1>(), s>>>(P);
+  else if (two_tile) tc_trunk2_kernel<false, 1><<<grid, NTHREADS, smem2_bytes<1>(), s>>>(P);
   else if (P.x3 && f16) tc_trunk_kernel<true, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else if (P.x3) tc_trunk_kernel<true, false><<<grid, NTHREADS, smem_bytes(), s>>>(P);
   else if (f16) tc_trunk_kernel<false, true><<<grid, NTHREADS, smem_bytes(), s>>>(P);

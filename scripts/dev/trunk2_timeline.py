@@ -41,6 +41,7 @@ buf = (C.c_longlong * 8192)()
 lib.dgdm_trunk_trace_read.argtypes = [C.POINTER(C.c_longlong), C.c_int32]
 assert lib.dgdm_trunk_trace_read(buf, 8192) == 0
 tr = np.array(buf[:], dtype=np.int64)
+print("DGDM_TRUNK2 =", os.environ.get("DGDM_TRUNK2"))
 n_m = (34 if is3d else 30)
 n_e = (36 if is3d else 32)
 t0 = min(int(v) for v in tr[:4096] if v > 0)

@@ -617,18 +617,20 @@ def test_kernel_variants_are_bit_identical(tmp_path):
     """Three builds of the same arithmetic must agree bit for bit in gradients and scores:
     the default path (a CTA owns a contiguous tile range and adds a pair's per-tile sums up itself, cut pairs fixed up);
     DGDM_TRUNK_SLOTS=1, the round-1 reduction (one slot per (pair, tile) + reduce_slots_kernel): same ascending-tile order;
-    DGDM_TRUNK2=1, the two-tile SS-mode kernel for the single-pass modes: same operands, same K order, same reduction."""
+    DGDM_TRUNK2=1, the two-tile SS-mode kernel for the single-pass modes: same operands, same K order, same reduction;
+    DGDM_TRUNK2=2, its CTA-pair form (cta_group::2 MMAs over two SMs, each CTA staging half of every weight tile)."""
     import os
     import subprocess
     import sys
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for name, env in (("default", {}), ("slots", {"DGDM_TRUNK_SLOTS": "1"}), ("two_tile", {"DGDM_TRUNK2": "1"})):
+    for name, env in (("default", {}), ("slots", {"DGDM_TRUNK_SLOTS": "1"}), ("two_tile", {"DGDM_TRUNK2": "1"}),
+                      ("two_tile_pair", {"DGDM_TRUNK2": "2"})):
         path = str(tmp_path / f"variant_{name}.pt")
         r = subprocess.run([sys.executable, "-c", _TRUNK2_SCRIPT, repo, path], capture_output=True, text=True, timeout=600,
                            env=dict(os.environ, **env))
         assert r.returncode == 0, (name, r.stderr[-3000:])
         res[name] = torch.load(path)
-    for name in ("slots", "two_tile"):
+    for name in ("slots", "two_tile", "two_tile_pair"):
         for k in res["default"]:
             assert torch.equal(res["default"][k], res[name][k]), (name, k, float((res["default"][k] - res[name][k]).abs().max()))
