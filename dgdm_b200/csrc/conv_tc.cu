@@ -235,13 +235,15 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
               const float v0 = __uint_as_float(rr[i + 2 * e]) + bv.x, v1 = __uint_as_float(rr[i + 2 * e + 1]) + bv.y;
               __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
               hi[e] = *reinterpret_cast<uint32_t*>(&h);
-              const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xFFFF0000u);
-              __nv_bfloat162 lw = __floats2bfloat162_rn(v0 - h0, v1 - h1);
-              lo[e] = *reinterpret_cast<uint32_t*>(&lw);
+              if (P.x3) {                         // (single-pass mode: the next conv reads only the hi plane)
+                const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xFFFF0000u);
+                __nv_bfloat162 lw = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+                lo[e] = *reinterpret_cast<uint32_t*>(&lw);
+              }
             }
             const int64_t off = (int64_t)(P.o_chunk0 + ((c + i) >> 3)) * P.o_plane + prow * 16;
             *reinterpret_cast<uint4*>(P.o_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(P.o_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (P.x3) *reinterpret_cast<uint4*>(P.o_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }

@@ -313,6 +313,7 @@ struct Gn2Args {
   int out_mode;                                              // 0 chunk-major, 1 even/odd positions split into two channel halves, 2 fused 1x1 output conv
   uint8_t* o_hi; uint8_t* o_lo; int64_t o_plane; int o_chunk0;
   const float* p_w; const float* p_b; float* eps;
+  int x3;                                                    // 0: single-pass mode, the convs read only the hi plane: no lo work
 };
 
 // GroupNorm(8) + Mish (+ FiLM) (+ residual) for one sample per CTA, one warp per group.  A lane item is 8 channels
@@ -385,7 +386,8 @@ __global__ void __launch_bounds__(256) gn2_kernel(Gn2Args a) {
     }
     if (a.res_mode == 1) {
       const int64_t off = (int64_t)(a.r_chunk0 + chunk) * a.r_plane + (4 + b * Lp + l) * 16;
-      const uint4 h = *reinterpret_cast<const uint4*>(a.r_hi + off), lw = *reinterpret_cast<const uint4*>(a.r_lo + off);
+      const uint4 h = *reinterpret_cast<const uint4*>(a.r_hi + off);
+      const uint4 lw = a.x3 ? *reinterpret_cast<const uint4*>(a.r_lo + off) : make_uint4(0u, 0u, 0u, 0u);
       const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lv[4] = {lw.x, lw.y, lw.z, lw.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -412,15 +414,17 @@ __global__ void __launch_bounds__(256) gn2_kernel(Gn2Args a) {
       for (int e = 0; e < 4; ++e) {
         __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * e], y[2 * e + 1]);
         hi[e] = *reinterpret_cast<uint32_t*>(&h);
-        const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xFFFF0000u);
-        __nv_bfloat162 lw = __floats2bfloat162_rn(y[2 * e] - h0, y[2 * e + 1] - h1);
-        lo[e] = *reinterpret_cast<uint32_t*>(&lw);
+        if (a.x3) {
+          const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xFFFF0000u);
+          __nv_bfloat162 lw = __floats2bfloat162_rn(y[2 * e] - h0, y[2 * e + 1] - h1);
+          lo[e] = *reinterpret_cast<uint32_t*>(&lw);
+        }
       }
       int64_t off;
       if (a.out_mode == 0) off = (int64_t)(a.o_chunk0 + chunk) * a.o_plane + (4 + b * Lp + l) * 16;
       else off = (int64_t)(a.o_chunk0 + (l & 1) * (a.C / 8) + chunk) * a.o_plane + (4 + b * (a.L / 2 + 2) + (l >> 1)) * 16;
       *reinterpret_cast<uint4*>(a.o_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(a.o_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (a.x3) *reinterpret_cast<uint4*>(a.o_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
   if (a.out_mode == 2) {      // final_conv.1 (Conv1d(128,1,1)): fixed-order sum over groups and chunks -> deterministic
@@ -488,7 +492,7 @@ int res_block_tc(const TcRun& R, const TcBufs& B, int bi, const ActBuf& in, int 
   }
   Gn2Args g0{};
   g0.in = B.t0; g0.in_rows = R.n * L; g0.gamma = w.gn0_w; g0.beta = w.gn0_b; g0.film = B.film[bi]; g0.n = R.n; g0.L = L; g0.C = co;
-  g0.res_mode = 0; g0.out_mode = 0; g0.o_hi = h.hi; g0.o_lo = h.lo; g0.o_plane = h.plane; g0.o_chunk0 = 0;
+  g0.x3 = R.x3; g0.res_mode = 0; g0.out_mode = 0; g0.o_hi = h.hi; g0.o_lo = h.lo; g0.o_plane = h.plane; g0.o_chunk0 = 0;
   DGDM_TRY(launch_gn2(g0, R.s));
   DGDM_TRY(conv_to_f32(R, h, 0, co, 5, 0, R.pl.conv1[bi], w.conv1_b, co, L, B.t1));
   Gn2Args g1{};
@@ -501,7 +505,7 @@ int res_block_tc(const TcRun& R, const TcBufs& B, int bi, const ActBuf& in, int 
   } else {
     g1.res_mode = 1; g1.r_hi = in.hi; g1.r_lo = in.lo; g1.r_plane = in.plane; g1.r_chunk0 = in_chunk0;
   }
-  g1.out_mode = out_mode; g1.o_hi = out.hi; g1.o_lo = out.lo; g1.o_plane = out.plane; g1.o_chunk0 = out_chunk0;
+  g1.x3 = R.x3; g1.out_mode = out_mode; g1.o_hi = out.hi; g1.o_lo = out.lo; g1.o_plane = out.plane; g1.o_chunk0 = out_chunk0;
   DGDM_TRY(launch_gn2(g1, R.s));
   return DGDM_OK;
 }
@@ -583,7 +587,7 @@ int unet_forward_tc(const dgdm_unet_weights* w, const float* x, int64_t n, int P
     DGDM_TRY(conv_to_f32(R, B.f1, 0, 128, 5, 0, R.pl.fin, w->fin_b, 128, L, B.t0));
     Gn2Args gf{};
     gf.in = B.t0; gf.in_rows = m * L; gf.gamma = w->fin_gn_w; gf.beta = w->fin_gn_b; gf.film = nullptr; gf.n = m; gf.L = L; gf.C = 128;
-    gf.res_mode = 0; gf.out_mode = 2; gf.p_w = w->out_w; gf.p_b = w->out_b; gf.eps = eps + n0 * L;
+    gf.x3 = R.x3; gf.res_mode = 0; gf.out_mode = 2; gf.p_w = w->out_w; gf.p_b = w->out_b; gf.eps = eps + n0 * L;
     DGDM_TRY(launch_gn2(gf, s));
   }
   return DGDM_OK;
