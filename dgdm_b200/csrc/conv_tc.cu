@@ -10,8 +10,14 @@
 //   warp 9   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 x N x K=16.  A descriptor = K-major, no swizzle,
 //            start address advanced by 16 bytes per tap row; B descriptor = K-major SWIZZLE_128B.  fp32 accumulators
 //            in TMEM, double-buffered (2 x 256 columns).  fp32-grade mode issues hi.hi, lo.hi, hi.lo.
-//   warps 0-7 epilogue: tcgen05.ld, + bias, then either fp32 "quad-major" rows for the GroupNorm kernel or bf16
-//            hi/lo chunk-major rows for the next conv (Downsample1d / Upsample1d outputs, which have no norm).
+//   warps 0-15 epilogue (warp w: TMEM lanes 32 (w % 4).., column quarter w / 4): tcgen05.ld, + bias, then
+//            mode 0  fp32 "quad-major" rows (the 1x1 residual convs, and the unfused GroupNorm path),
+//            mode 1  bf16 hi/lo chunk-major rows for the next conv (Downsample1d / Upsample1d outputs: no norm),
+//            mode 2/3  GroupNorm(8) + Mish (+ FiLM) (+ residual) on the accumulator itself: tiles are aligned to whole
+//                    samples, pass 1 reads the accumulator for per-(row, group) mean / M2, one thread per (sample, group)
+//                    combines them in a fixed order, pass 2 reads the accumulator again, normalises and writes bf16
+//                    chunk-major rows for the next conv (or the fused 1x1 output conv).  The conv output never goes to
+//                    HBM in fp32 and there is no separate GroupNorm launch.
 #include <cuda_bf16.h>
 
 #include "conv_tc.cuh"
@@ -20,7 +26,8 @@ namespace dgdm {
 namespace {
 
 constexpr int TM = 128, SLAB_ROWS = TM + 4, PLANE_B = SLAB_ROWS * 16, SLAB_B = 8 * PLANE_B, A_STAGE_B = 2 * SLAB_B;
-constexpr int NEPI = 8, NTHR = (NEPI + 2) * 32;
+constexpr int NEPI = 16, NTHR = (NEPI + 2) * 32;
+constexpr int GN_MAX_S = 44;
 constexpr int MAX_W = 6, MAX_A = 3;
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,6 +90,145 @@ struct Bars {
   uint64_t a_full[MAX_A], a_empty[MAX_A], w_full[MAX_W], w_empty[MAX_W], d_full[2], d_empty[2];
   uint32_t tmem_base, pad_;
 };
+// per-channel parameters and the statistics exchange of the fused GroupNorm epilogue
+struct GnShared {
+  float bias[256], gamma[256], beta[256], fs[256], ft[256], rw[256], rb[256], pw[256];
+  float2 part[TM][8];          // (mean, M2) of one row's channels of one group
+  float2 stat[GN_MAX_S][8];    // (mean, rstd) of one (sample, group)
+  float proj[4][TM];
+};
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory"); }
+
+// GroupNorm(8) + Mish (+ FiLM) (+ residual) epilogue of one tile; GW = channels per group (16: N = 128, 32: N = 256)
+template <int GW>
+__device__ __forceinline__ void epilogue_gn(const ConvTcParams& P, GnShared& G, uint32_t taddr, int c_lo, int ncol, int r,
+                                            int part, int etid, int64_t tile) {
+  const int Lp = P.Ld + 2;
+  const int bs = r / Lp, l = r - bs * Lp;
+  const int64_t b = tile * P.gn_S + bs;
+  const bool live = bs < P.gn_S && l < P.Ld && b < P.n;
+  // ---- pass 1: per-row, per-group mean and centred sum of squares
+#pragma unroll 1
+  for (int c = c_lo; c < c_lo + ncol; c += 32) {
+    uint32_t rr[32];
+    ld32(taddr + (uint32_t)c, rr);
+    if (!live) continue;
+#pragma unroll
+    for (int h = 0; h < 32 / GW; ++h) {
+      float v[GW], s = 0.f;
+#pragma unroll
+      for (int i = 0; i < GW; i += 4) {
+        const float4 bv = *reinterpret_cast<const float4*>(&G.bias[c + h * GW + i]);
+        v[i] = __uint_as_float(rr[h * GW + i]) + bv.x; v[i + 1] = __uint_as_float(rr[h * GW + i + 1]) + bv.y;
+        v[i + 2] = __uint_as_float(rr[h * GW + i + 2]) + bv.z; v[i + 3] = __uint_as_float(rr[h * GW + i + 3]) + bv.w;
+        s += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+      }
+      const float m = s * (1.f / GW);
+      float m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < GW; ++i) { const float d = v[i] - m; m2 = fmaf(d, d, m2); }
+      G.part[r][(c + h * GW) / GW] = make_float2(m, m2);
+    }
+  }
+  epi_sync();
+  // ---- one thread per (sample, group): equal-count blocks, so the mean is the mean of the row means and
+  //      M2 = sum_i M2_i + GW (m_i - mean)^2, summed in position order (deterministic)
+  for (int e = etid; e < P.gn_S * 8; e += NEPI * 32) {
+    const int sb = e >> 3, g = e & 7, r0 = sb * Lp;
+    if (tile * P.gn_S + sb < P.n) {
+      float sm = 0.f;
+      for (int l2 = 0; l2 < P.Ld; ++l2) sm += G.part[r0 + l2][g].x;
+      const float mean = sm / (float)P.Ld;
+      float m2 = 0.f;
+      for (int l2 = 0; l2 < P.Ld; ++l2) {
+        const float2 pm = G.part[r0 + l2][g];
+        const float d = pm.x - mean;
+        m2 += fmaf((float)GW * d, d, pm.y);
+      }
+      G.stat[sb][g] = make_float2(mean, rsqrtf(m2 / (float)(P.Ld * GW) + 1e-5f));
+    }
+  }
+  epi_sync();
+  // ---- pass 2: normalise, Mish, FiLM, residual, write
+  const int64_t crow = b * P.Ld + l;                                                    // compact row
+  const int64_t prow = 4 + b * Lp + l;                                                  // physical row (input / residual)
+  const int64_t orow = P.o_split ? 4 + b * (P.Ld / 2 + 2) + (l >> 1) : prow;            // physical output row
+  const int o_chunk = P.o_chunk0 + (P.o_split ? (l & 1) * (P.N / 8) : 0);
+  const float xin = (live && P.res_mode == 3) ? P.r_x[crow] : 0.f;
+  float proj = 0.f;
+#pragma unroll 1
+  for (int c = c_lo; c < c_lo + ncol; c += 32) {
+    uint32_t rr[32];
+    ld32(taddr + (uint32_t)c, rr);
+    if (!live) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = c + 8 * j, chunk = ch >> 3;
+      const float2 st = G.stat[bs][ch / GW];
+      float y[8];
+#pragma unroll
+      for (int e4 = 0; e4 < 8; e4 += 4) {
+        const float4 bv = *reinterpret_cast<const float4*>(&G.bias[ch + e4]);
+        const float4 gm = *reinterpret_cast<const float4*>(&G.gamma[ch + e4]);
+        const float4 bt = *reinterpret_cast<const float4*>(&G.beta[ch + e4]);
+        const float4 fs = *reinterpret_cast<const float4*>(&G.fs[ch + e4]);
+        const float4 ft = *reinterpret_cast<const float4*>(&G.ft[ch + e4]);
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, gg[4] = {gm.x, gm.y, gm.z, gm.w}, tt[4] = {bt.x, bt.y, bt.z, bt.w};
+        const float f0[4] = {fs.x, fs.y, fs.z, fs.w}, f1[4] = {ft.x, ft.y, ft.z, ft.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v = __uint_as_float(rr[8 * j + e4 + e]) + bb[e];
+          const float sc = st.y * gg[e];
+          y[e4 + e] = fmaf(f0[e], mish_fast(fmaf(v, sc, fmaf(-st.x, sc, tt[e]))), f1[e]);
+        }
+      }
+      if (P.res_mode == 1) {
+        const int64_t off = (int64_t)(P.r_chunk0 + chunk) * P.r_plane + prow * 16;
+        const uint4 h = *reinterpret_cast<const uint4*>(P.r_hi + off);
+        const uint4 lw = P.x3 ? *reinterpret_cast<const uint4*>(P.r_lo + off) : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lv[4] = {lw.x, lw.y, lw.z, lw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          y[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lv[e] << 16);
+          y[2 * e + 1] += __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lv[e] & 0xFFFF0000u);
+        }
+      } else if (P.res_mode == 2) {
+        const float4 r0 = *reinterpret_cast<const float4*>(P.r_f32 + ((int64_t)(2 * chunk) * P.r_rows + crow) * 4);
+        const float4 r1 = *reinterpret_cast<const float4*>(P.r_f32 + ((int64_t)(2 * chunk + 1) * P.r_rows + crow) * 4);
+        y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w; y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+      } else if (P.res_mode == 3) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] += fmaf(G.rw[ch + e], xin, G.rb[ch + e]);
+      }
+      if (P.out_mode == 3) {
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d = fmaf(y[e], G.pw[ch + e], d);
+        proj += d;
+      } else {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * e], y[2 * e + 1]);
+          hi[e] = *reinterpret_cast<uint32_t*>(&h);
+          if (P.x3) {
+            const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xFFFF0000u);
+            __nv_bfloat162 lw = __floats2bfloat162_rn(y[2 * e] - h0, y[2 * e + 1] - h1);
+            lo[e] = *reinterpret_cast<uint32_t*>(&lw);
+          }
+        }
+        const int64_t off = (int64_t)(o_chunk + chunk) * P.o_plane + orow * 16;
+        *reinterpret_cast<uint4*>(P.o_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (P.x3) *reinterpret_cast<uint4*>(P.o_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+  if (P.out_mode == 3) {      // Conv1d(N,1,1): the four column quarters of a row are summed in a fixed order
+    G.proj[part][r] = proj;
+    epi_sync();
+    if (part == 0 && live) P.eps[crow] = P.p_b[0] + ((G.proj[0][r] + G.proj[1][r]) + (G.proj[2][r] + G.proj[3][r]));
+  }
+}
 
 __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
   extern __shared__ uint8_t raw[];
@@ -90,6 +236,7 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
   uint8_t* wring = raw + ((1024u - (s32(raw) & 1023u)) & 1023u);       // 1024-byte aligned, shared address space kept
   uint8_t* aring = wring + (size_t)P.n_w * w_tile;
   Bars& S = *reinterpret_cast<Bars*>(aring + (size_t)P.n_a * A_STAGE_B);
+  GnShared& G = *reinterpret_cast<GnShared*>(aring + (size_t)P.n_a * A_STAGE_B + ((sizeof(Bars) + 15) & ~(size_t)15));
   // warp index through a shuffle: provably warp-uniform for the compiler (see the MMA issuer)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
@@ -98,6 +245,14 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
     for (int s = 0; s < P.n_w; ++s) { bar_init(&S.w_full[s], 1); bar_init(&S.w_empty[s], 1); }
     for (int i = 0; i < 2; ++i) { bar_init(&S.d_full[i], 1); bar_init(&S.d_empty[i], NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (P.out_mode >= 2) {
+    for (int i = tid; i < P.N; i += NTHR) {
+      G.bias[i] = P.bias ? P.bias[i] : 0.f; G.gamma[i] = P.gamma[i]; G.beta[i] = P.beta[i];
+      G.fs[i] = P.film ? P.film[i] : 1.f; G.ft[i] = P.film ? P.film[P.N + i] : 0.f;
+      G.rw[i] = P.res_mode == 3 ? P.r_w[i] : 0.f; G.rb[i] = P.res_mode == 3 ? P.r_b[i] : 0.f;
+      G.pw[i] = P.out_mode == 3 ? P.p_w[i] : 0.f;
+    }
   }
   if (warp == NEPI + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(&S.tmem_base)) : "memory");
@@ -116,7 +271,7 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
     if (lane == 0) {
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        const int64_t f0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TM;
+        const int64_t f0 = P.f_base + ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * P.tile_rows;
         for (int c = 0; c < P.n_cb; ++c) {
           const ConvTcBlock& cb = P.cb[c];
           bar_wait(&S.a_empty[sa], pa ^ 1, P.err, 21);
@@ -194,23 +349,28 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
       }
     }
   } else {
-    // ------------------------------- epilogue warps 0..7 -------------------------------
-    const int q = warp & 3, half = warp >> 2;
+    // ------------------------------- epilogue warps 0..15 -------------------------------
+    const int q = warp & 3, part = warp >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int Lp = P.Ld + 2;
-    const int ncol = P.N / 2, c_lo = half * ncol;
+    const int ncol = P.N / (NEPI / 4), c_lo = part * ncol;
     for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
-      const int64_t f = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TM + r;    // output physical row = f + 2
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+      bar_wait(&S.d_full[acc], (t >> 1) & 1, P.err, 27);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (P.out_mode >= 2) {
+        if (P.N == 128) epilogue_gn<16>(P, G, lane_addr + (uint32_t)acc * 256u, c_lo, ncol, r, part, tid, tile);
+        else epilogue_gn<32>(P, G, lane_addr + (uint32_t)acc * 256u, c_lo, ncol, r, part, tid, tile);
+      } else {
+      const int64_t f = tile * TM + r;                                                 // output physical row = f + 2
       const int64_t qf = f - 2;
       const int64_t b = qf >= 0 ? qf / Lp : 0;
       const int l = (int)(qf - b * Lp);
       const bool live = qf >= 0 && l < P.Ld && b < P.n;
       const int64_t orow = b * P.Lo + (int64_t)l * P.o_step + P.o_off;               // compact row (mode 0)
       const int64_t prow = 4 + b * (P.Lo + 2) + (int64_t)l * P.o_step + P.o_off;       // physical row (mode 1)
-      bar_wait(&S.d_full[acc], (t >> 1) & 1, P.err, 27);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int c = c_lo; c < c_lo + ncol; c += 32) {
         uint32_t rr[32];
@@ -247,6 +407,7 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
           }
         }
       }
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) bar_arrive(&S.d_empty[acc]);
@@ -278,8 +439,9 @@ int conv_tc_launch(ConvTcParams& P, cudaStream_t s) {
   int dev = 0;
   DGDM_CUDA(cudaGetDevice(&dev));
   DGDM_CHECK_ARG(dev >= 0 && dev < 64, "conv_tc: device ordinal %d out of range", dev);
-  const int smem_256 = 1024 + 4 * 256 * 128 + 2 * A_STAGE_B + (int)sizeof(Bars);
-  const int smem_128 = 1024 + 6 * 128 * 128 + 3 * A_STAGE_B + (int)sizeof(Bars);
+  const int tail = (int)(((sizeof(Bars) + 15) & ~(size_t)15) + sizeof(GnShared));
+  const int smem_256 = 1024 + 4 * 256 * 128 + 2 * A_STAGE_B + tail;
+  const int smem_128 = 1024 + 6 * 128 * 128 + 3 * A_STAGE_B + tail;
   const int max_smem = smem_256 > smem_128 ? smem_256 : smem_128;
   if (sm_counts[dev] == 0) {
     int n = 0;
@@ -290,8 +452,18 @@ int conv_tc_launch(ConvTcParams& P, cudaStream_t s) {
   const int sm_count = sm_counts[dev];
   P.n_w = P.N == 256 ? 4 : 6;
   P.n_a = P.N == 256 ? 2 : 3;
-  P.n_tiles = (int)((2 + P.n * (P.Ld + 2) + TM - 1) / TM);
-  const size_t smem = 1024 + (size_t)P.n_w * P.N * 128 + (size_t)P.n_a * A_STAGE_B + sizeof(Bars);
+  if (P.out_mode >= 2) {
+    DGDM_CHECK_ARG(P.Ld >= 1 && P.Ld + 2 <= TM && P.gamma && P.beta && P.o_step == 1 && P.o_off == 0 && P.Lo == P.Ld,
+                   "conv_tc: fused GroupNorm needs whole samples per tile (Ld=%d) and a unit-stride output", P.Ld);
+    P.gn_S = TM / (P.Ld + 2);
+    DGDM_CHECK_ARG(P.gn_S <= GN_MAX_S, "conv_tc: %d samples per tile", P.gn_S);
+    P.tile_rows = P.gn_S * (P.Ld + 2); P.f_base = 2;
+    P.n_tiles = (int)((P.n + P.gn_S - 1) / P.gn_S);
+  } else {
+    P.gn_S = 0; P.tile_rows = TM; P.f_base = 0;
+    P.n_tiles = (int)((2 + P.n * (P.Ld + 2) + TM - 1) / TM);
+  }
+  const size_t smem = 1024 + (size_t)P.n_w * P.N * 128 + (size_t)P.n_a * A_STAGE_B + (size_t)tail;
   DGDM_CHECK_ARG(smem <= (size_t)max_smem, "conv_tc: shared memory plan %zu exceeds %d", smem, max_smem);
   const int grid = P.n_tiles < sm_count ? P.n_tiles : sm_count;
   conv_tc_kernel<<<grid, NTHR, smem, s>>>(P);

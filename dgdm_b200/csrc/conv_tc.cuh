@@ -18,7 +18,8 @@ struct ActBuf {
   uint8_t* hi; uint8_t* lo;
   int64_t plane;      // bytes per chunk plane = rows * 16
 };
-inline int64_t act_rows(int64_t n, int L) { return ((2 + n * (L + 2)) + 127) / 128 * 128 + 8; }
+// (+136: the sample-aligned tiles of the fused GroupNorm mode start at row 2 + b0 * (L + 2) and stage 132 rows)
+inline int64_t act_rows(int64_t n, int L) { return ((2 + n * (L + 2)) + 127) / 128 * 128 + 136; }
 
 struct ConvTcTap { uint16_t roff, wkb; };                 // A row offset (tap shift), weight k-block index in the image
 struct ConvTcBlock { uint16_t chunk0, ntap; ConvTcTap tap[5]; };   // one 64-channel block of the A operand
@@ -33,13 +34,36 @@ struct ConvTcParams {
   int Ld;                       // positions per sample in the compute domain (period Ld + 2)
   int n_tiles;
   // output: row l of sample b goes to output position l * o_step + o_off of a sample with Lo positions
-  int out_mode;                 // 0: fp32 quad-major compact [C/4][n*Lo][4]; 1: bf16 hi/lo chunk-major
+  int out_mode;                 // 0: fp32 quad-major compact [C/4][n*Lo][4]; 1: bf16 hi/lo chunk-major;
+                                // 2: GroupNorm(8) + Mish (+ FiLM) (+ residual) in the epilogue -> bf16 hi/lo chunk-major;
+                                // 3: the same, then the 1x1 output conv (Conv1d(N,1,1)) -> eps
   float* o_f32; int64_t o_rows;
   uint8_t* o_hi; uint8_t* o_lo; int64_t o_plane; int o_chunk0;
   int Lo, o_step, o_off;
   int n_w, n_a;                 // ring depths
   int* err;
+  // ---- out_mode 2 / 3 (Conv1dBlock, diffusion_utils.py:80-97, and the tail of ConditionalResidualBlock1D, :100-120).
+  // A tile holds gn_S = 128 / (Ld + 2) WHOLE samples (tile_rows = gn_S * (Ld + 2) of the 128 MMA rows are used), so the
+  // statistics of a (sample, group) never leave the CTA.  o_step = 1, o_off = 0, Lo = Ld.
+  int gn_S, tile_rows, f_base;  // set by conv_tc_launch (modes 0 / 1: tile_rows = 128, f_base = 0)
+  const float* gamma; const float* beta; const float* film;   // film: [2N] (scale | shift) or null
+  int res_mode;                 // 0 none, 1 chunk-major bf16, 2 fp32 quad-major [N/4][r_rows][4], 3 Cin=1 1x1 conv of x
+  const uint8_t* r_hi; const uint8_t* r_lo; int64_t r_plane; int r_chunk0;
+  const float* r_f32; int64_t r_rows;
+  const float* r_x; const float* r_w; const float* r_b;
+  int o_split;                  // 1: even / odd positions go to two channel halves of a half-length buffer (for the strided conv)
+  const float* p_w; const float* p_b; float* eps;             // mode 3
 };
+
+#ifdef __CUDACC__
+// mish for the tensor-core path: ex2.approx + rcp.approx (2^-21-grade, far inside that path's tolerance); the clamp
+// makes x >= 20 return x exactly (n/(n+2) rounds to 1) without a branch and keeps e finite.
+__device__ __forceinline__ float mish_fast(float x) {
+  const float e = __expf(fminf(x, 20.f));
+  const float n = fmaf(e, e, e + e);
+  return x * __fdividef(n, n + 2.f);
+}
+#endif
 
 // standard conv: `taps` taps over `cin` channels starting at chunk `in_chunk0`, first tap at row offset `roff0`
 void conv_tc_blocks(ConvTcParams& P, int in_chunk0, int cin, int taps, int roff0);
