@@ -27,6 +27,7 @@ namespace {
 
 constexpr int TM = 128, SLAB_ROWS = TM + 4, PLANE_B = SLAB_ROWS * 16, SLAB_B = 8 * PLANE_B, A_STAGE_B = 2 * SLAB_B;
 constexpr int NEPI = 16, NTHR = (NEPI + 2) * 32;
+constexpr int NG = 1, GW_WARPS = NEPI / NG, NPART = GW_WARPS / 4;   // epilogue groups (see the epilogue), warps per group, column parts per group
 constexpr int GN_MAX_S = 44;
 constexpr int MAX_W = 6, MAX_A = 3;
 
@@ -86,23 +87,36 @@ __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 struct Bars {
   uint64_t a_full[MAX_A], a_empty[MAX_A], w_full[MAX_W], w_empty[MAX_W], d_full[2], d_empty[2];
   uint32_t tmem_base, pad_;
 };
-// per-channel parameters and the statistics exchange of the fused GroupNorm epilogue
+// per-channel parameters and the statistics exchange of the fused GroupNorm epilogue ([NG]: one per epilogue group)
 struct GnShared {
-  float bias[256], gamma[256], beta[256], fs[256], ft[256], rw[256], rb[256], pw[256];
-  float2 part[TM][8];          // (mean, M2) of one row's channels of one group
-  float2 stat[GN_MAX_S][8];    // (mean, rstd) of one (sample, group)
-  float proj[4][TM];
+  float bias[256], gamma[256], beta[256];
+  float x0[256], x1[256];           // FiLM scale | shift (conv0), or the Cin=1 residual conv's weight | bias (res_mode 3), or the 1x1 output conv's weight (mode 3) | -
+  float2 part[NG][8][TM + 1];       // (mean, M2) of one row's channels of one group
+  float2 stat[NG][GN_MAX_S][8];     // (mean, rstd) of one (sample, group)
+  float proj[NG][NPART][TM];
 };
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory"); }
+constexpr int NGRP = GW_WARPS * 32;  // threads of one epilogue group
+__device__ __forceinline__ void epi_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NGRP) : "memory"); }
 
 // GroupNorm(8) + Mish (+ FiLM) (+ residual) epilogue of one tile; GW = channels per group (16: N = 128, 32: N = 256)
 template <int GW>
 __device__ __forceinline__ void epilogue_gn(const ConvTcParams& P, GnShared& G, uint32_t taddr, int c_lo, int ncol, int r,
-                                            int part, int etid, int64_t tile) {
+                                            int part, int etid, int grp, int64_t tile) {
   const int Lp = P.Ld + 2;
   const int bs = r / Lp, l = r - bs * Lp;
   const int64_t b = tile * P.gn_S + bs;
@@ -112,7 +126,7 @@ __device__ __forceinline__ void epilogue_gn(const ConvTcParams& P, GnShared& G, 
   for (int c = c_lo; c < c_lo + ncol; c += 32) {
     uint32_t rr[32];
     ld32(taddr + (uint32_t)c, rr);
-    if (!live) continue;
+    if (live) {
 #pragma unroll
     for (int h = 0; h < 32 / GW; ++h) {
       float v[GW], s = 0.f;
@@ -123,38 +137,50 @@ __device__ __forceinline__ void epilogue_gn(const ConvTcParams& P, GnShared& G, 
         v[i + 2] = __uint_as_float(rr[h * GW + i + 2]) + bv.z; v[i + 3] = __uint_as_float(rr[h * GW + i + 3]) + bv.w;
         s += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
       }
+#pragma unroll
+      for (int i = 0; i < GW; ++i) rr[h * GW + i] = __float_as_uint(v[i]);
       const float m = s * (1.f / GW);
       float m2 = 0.f;
 #pragma unroll
       for (int i = 0; i < GW; ++i) { const float d = v[i] - m; m2 = fmaf(d, d, m2); }
-      G.part[r][(c + h * GW) / GW] = make_float2(m, m2);
+      G.part[grp][(c + h * GW) / GW][r] = make_float2(m, m2);
     }
+    }
+    st32(taddr + (uint32_t)c, rr);      // accumulator + bias goes back to TMEM: pass 2 re-reads it without the add
   }
-  epi_sync();
+  epi_sync(grp);
   // ---- one thread per (sample, group): equal-count blocks, so the mean is the mean of the row means and
-  //      M2 = sum_i M2_i + GW (m_i - mean)^2, summed in position order (deterministic)
-  for (int e = etid; e < P.gn_S * 8; e += NEPI * 32) {
-    const int sb = e >> 3, g = e & 7, r0 = sb * Lp;
+  //      M2 = sum_i M2_i + GW (m_i - mean)^2, summed in a fixed order (deterministic)
+  for (int e = etid; e < P.gn_S * 8; e += NGRP) {
+    const int sb = e >> 3, g = e & 7;
     if (tile * P.gn_S + sb < P.n) {
-      float sm = 0.f;
-      for (int l2 = 0; l2 < P.Ld; ++l2) sm += G.part[r0 + l2][g].x;
-      const float mean = sm / (float)P.Ld;
-      float m2 = 0.f;
-      for (int l2 = 0; l2 < P.Ld; ++l2) {
-        const float2 pm = G.part[r0 + l2][g];
-        const float d = pm.x - mean;
-        m2 += fmaf((float)GW * d, d, pm.y);
+      const float2* pr = &G.part[grp][g][sb * Lp];
+      float s0 = 0.f, s1 = 0.f;
+      int l2 = 0;
+#pragma unroll 4
+      for (; l2 + 1 < P.Ld; l2 += 2) { s0 += pr[l2].x; s1 += pr[l2 + 1].x; }
+      if (l2 < P.Ld) s0 += pr[l2].x;
+      const float mean = (s0 + s1) / (float)P.Ld;
+      float a0 = 0.f, a1 = 0.f;
+      l2 = 0;
+#pragma unroll 4
+      for (; l2 + 1 < P.Ld; l2 += 2) {
+        const float2 p0 = pr[l2], p1 = pr[l2 + 1];
+        const float d0 = p0.x - mean, d1 = p1.x - mean;
+        a0 += fmaf((float)GW * d0, d0, p0.y); a1 += fmaf((float)GW * d1, d1, p1.y);
       }
-      G.stat[sb][g] = make_float2(mean, rsqrtf(m2 / (float)(P.Ld * GW) + 1e-5f));
+      if (l2 < P.Ld) { const float2 p0 = pr[l2]; const float d0 = p0.x - mean; a0 += fmaf((float)GW * d0, d0, p0.y); }
+      G.stat[grp][sb][g] = make_float2(mean, rsqrtf((a0 + a1) / (float)(P.Ld * GW) + 1e-5f));
     }
   }
-  epi_sync();
+  epi_sync(grp);
   // ---- pass 2: normalise, Mish, FiLM, residual, write
   const int64_t crow = b * P.Ld + l;                                                    // compact row
   const int64_t prow = 4 + b * Lp + l;                                                  // physical row (input / residual)
   const int64_t orow = P.o_split ? 4 + b * (P.Ld / 2 + 2) + (l >> 1) : prow;            // physical output row
   const int o_chunk = P.o_chunk0 + (P.o_split ? (l & 1) * (P.N / 8) : 0);
   const float xin = (live && P.res_mode == 3) ? P.r_x[crow] : 0.f;
+  const bool film = P.film != nullptr;
   float proj = 0.f;
 #pragma unroll 1
   for (int c = c_lo; c < c_lo + ncol; c += 32) {
@@ -164,22 +190,22 @@ __device__ __forceinline__ void epilogue_gn(const ConvTcParams& P, GnShared& G, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ch = c + 8 * j, chunk = ch >> 3;
-      const float2 st = G.stat[bs][ch / GW];
+      const float2 st = G.stat[grp][bs][ch / GW];
       float y[8];
 #pragma unroll
       for (int e4 = 0; e4 < 8; e4 += 4) {
-        const float4 bv = *reinterpret_cast<const float4*>(&G.bias[ch + e4]);
         const float4 gm = *reinterpret_cast<const float4*>(&G.gamma[ch + e4]);
         const float4 bt = *reinterpret_cast<const float4*>(&G.beta[ch + e4]);
-        const float4 fs = *reinterpret_cast<const float4*>(&G.fs[ch + e4]);
-        const float4 ft = *reinterpret_cast<const float4*>(&G.ft[ch + e4]);
-        const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, gg[4] = {gm.x, gm.y, gm.z, gm.w}, tt[4] = {bt.x, bt.y, bt.z, bt.w};
+        const float4 fs = *reinterpret_cast<const float4*>(&G.x0[ch + e4]);
+        const float4 ft = *reinterpret_cast<const float4*>(&G.x1[ch + e4]);
+        const float gg[4] = {gm.x, gm.y, gm.z, gm.w}, tt[4] = {bt.x, bt.y, bt.z, bt.w};
         const float f0[4] = {fs.x, fs.y, fs.z, fs.w}, f1[4] = {ft.x, ft.y, ft.z, ft.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float v = __uint_as_float(rr[8 * j + e4 + e]) + bb[e];
+          const float v = __uint_as_float(rr[8 * j + e4 + e]);
           const float sc = st.y * gg[e];
-          y[e4 + e] = fmaf(f0[e], mish_fast(fmaf(v, sc, fmaf(-st.x, sc, tt[e]))), f1[e]);
+          const float mv = mish_fast(fmaf(v, sc, fmaf(-st.x, sc, tt[e])));
+          y[e4 + e] = film ? fmaf(f0[e], mv, f1[e]) : mv;
         }
       }
       if (P.res_mode == 1) {
@@ -198,12 +224,12 @@ __device__ __forceinline__ void epilogue_gn(const ConvTcParams& P, GnShared& G, 
         y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w; y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
       } else if (P.res_mode == 3) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] += fmaf(G.rw[ch + e], xin, G.rb[ch + e]);
+        for (int e = 0; e < 8; ++e) y[e] += fmaf(G.x0[ch + e], xin, G.x1[ch + e]);
       }
       if (P.out_mode == 3) {
         float d = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d = fmaf(y[e], G.pw[ch + e], d);
+        for (int e = 0; e < 8; ++e) d = fmaf(y[e], G.x0[ch + e], d);
         proj += d;
       } else {
         uint32_t hi[4], lo[4];
@@ -223,10 +249,29 @@ __device__ __forceinline__ void epilogue_gn(const ConvTcParams& P, GnShared& G, 
       }
     }
   }
-  if (P.out_mode == 3) {      // Conv1d(N,1,1): the four column quarters of a row are summed in a fixed order
-    G.proj[part][r] = proj;
-    epi_sync();
-    if (part == 0 && live) P.eps[crow] = P.p_b[0] + ((G.proj[0][r] + G.proj[1][r]) + (G.proj[2][r] + G.proj[3][r]));
+  if (P.out_mode == 3) {      // Conv1d(N,1,1): the column parts of a row are summed in a fixed order
+    G.proj[grp][part][r] = proj;
+    epi_sync(grp);
+    if (part == 0 && live) {
+      float d = G.proj[grp][0][r];
+#pragma unroll
+      for (int k = 1; k < NPART; ++k) d += G.proj[grp][k][r];
+      P.eps[crow] = P.p_b[0] + d;
+    }
+  } else if (bs < P.gn_S && l >= P.Ld && b < P.n) {
+    // the two rows after a sample: this kernel keeps them zero for the next conv (no separate memset of the buffer)
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int chunk = c_lo >> 3; chunk < (c_lo + ncol) >> 3; ++chunk) {
+      if (!P.o_split) {
+        const int64_t off = (int64_t)(P.o_chunk0 + chunk) * P.o_plane + prow * 16;
+        *reinterpret_cast<uint4*>(P.o_hi + off) = z;
+        if (P.x3) *reinterpret_cast<uint4*>(P.o_lo + off) = z;
+      } else {   // row Ld -> the even half's two pad rows, row Ld + 1 -> the odd half's
+        const int64_t off = (int64_t)(P.o_chunk0 + (l - P.Ld) * (P.N / 8) + chunk) * P.o_plane + (4 + b * (P.Ld / 2 + 2) + P.Ld / 2) * 16;
+        *reinterpret_cast<uint4*>(P.o_hi + off) = z; *reinterpret_cast<uint4*>(P.o_hi + off + 16) = z;
+        if (P.x3) { *reinterpret_cast<uint4*>(P.o_lo + off) = z; *reinterpret_cast<uint4*>(P.o_lo + off + 16) = z; }
+      }
+    }
   }
 }
 
@@ -243,15 +288,17 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
   if (tid == 0) {
     for (int s = 0; s < P.n_a; ++s) { bar_init(&S.a_full[s], 1); bar_init(&S.a_empty[s], 1); }
     for (int s = 0; s < P.n_w; ++s) { bar_init(&S.w_full[s], 1); bar_init(&S.w_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { bar_init(&S.d_full[i], 1); bar_init(&S.d_empty[i], NEPI); }
+    for (int i = 0; i < 2; ++i) { bar_init(&S.d_full[i], 1); bar_init(&S.d_empty[i], GW_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (P.out_mode >= 2) {
     for (int i = tid; i < P.N; i += NTHR) {
       G.bias[i] = P.bias ? P.bias[i] : 0.f; G.gamma[i] = P.gamma[i]; G.beta[i] = P.beta[i];
-      G.fs[i] = P.film ? P.film[i] : 1.f; G.ft[i] = P.film ? P.film[P.N + i] : 0.f;
-      G.rw[i] = P.res_mode == 3 ? P.r_w[i] : 0.f; G.rb[i] = P.res_mode == 3 ? P.r_b[i] : 0.f;
-      G.pw[i] = P.out_mode == 3 ? P.p_w[i] : 0.f;
+      float x0 = 1.f, x1 = 0.f;
+      if (P.film) { x0 = P.film[i]; x1 = P.film[P.N + i]; }
+      else if (P.res_mode == 3) { x0 = P.r_w[i]; x1 = P.r_b[i]; }
+      else if (P.out_mode == 3) x0 = P.p_w[i];
+      G.x0[i] = x0; G.x1[i] = x1;
     }
   }
   if (warp == NEPI + 1) {
@@ -350,31 +397,43 @@ __global__ void __launch_bounds__(NTHR, 1) conv_tc_kernel(const __grid_constant_
     }
   } else {
     // ------------------------------- epilogue warps 0..15 -------------------------------
-    const int q = warp & 3, part = warp >> 2;
-    const int r = q * 32 + lane;
+    // NG groups of NEPI / NG warps; group g takes this CTA's tiles g, g + NG, ...  (Measured: the epilogue is bound by
+    // issue slots, not latency -- two groups of eight warps were 20 % slower than one of sixteen, because a group then
+    // holds its accumulator twice as long and the MMAs of tile t + 2 wait for it.  NG = 1.)
+    const int grp = warp / GW_WARPS, w8 = warp % GW_WARPS;
+    const int q = w8 & 3, part = w8 >> 2;          // TMEM lane quarter = warp % 4
+    const int r = q * 32 + lane, etid = w8 * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int Lp = P.Ld + 2;
-    const int ncol = P.N / (NEPI / 4), c_lo = part * ncol;
-    for (int t = 0; t < my_tiles; ++t) {
+    const int ncol = P.N / NPART, c_lo = part * ncol;
+    for (int t = grp; t < my_tiles; t += NG) {
       const int acc = t & 1;
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
       bar_wait(&S.d_full[acc], (t >> 1) & 1, P.err, 27);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (P.out_mode >= 2) {
-        if (P.N == 128) epilogue_gn<16>(P, G, lane_addr + (uint32_t)acc * 256u, c_lo, ncol, r, part, tid, tile);
-        else epilogue_gn<32>(P, G, lane_addr + (uint32_t)acc * 256u, c_lo, ncol, r, part, tid, tile);
+        if (P.N == 128) epilogue_gn<16>(P, G, lane_addr + (uint32_t)acc * 256u, c_lo, ncol, r, part, etid, grp, tile);
+        else epilogue_gn<32>(P, G, lane_addr + (uint32_t)acc * 256u, c_lo, ncol, r, part, etid, grp, tile);
       } else {
       const int64_t f = tile * TM + r;                                                 // output physical row = f + 2
       const int64_t qf = f - 2;
       const int64_t b = qf >= 0 ? qf / Lp : 0;
       const int l = (int)(qf - b * Lp);
       const bool live = qf >= 0 && l < P.Ld && b < P.n;
+      const bool pad = P.out_mode == 1 && P.o_step == 1 && qf >= 0 && l >= P.Ld && b < P.n;   // rows after a sample stay zero
       const int64_t orow = b * P.Lo + (int64_t)l * P.o_step + P.o_off;               // compact row (mode 0)
       const int64_t prow = 4 + b * (P.Lo + 2) + (int64_t)l * P.o_step + P.o_off;       // physical row (mode 1)
 #pragma unroll 1
       for (int c = c_lo; c < c_lo + ncol; c += 32) {
         uint32_t rr[32];
         ld32(lane_addr + (uint32_t)acc * 256u + (uint32_t)c, rr);
+        if (pad) {
+          for (int i = 0; i < 32; i += 8) {
+            const int64_t off = (int64_t)(P.o_chunk0 + ((c + i) >> 3)) * P.o_plane + prow * 16;
+            *reinterpret_cast<uint4*>(P.o_hi + off) = make_uint4(0u, 0u, 0u, 0u);
+            if (P.x3) *reinterpret_cast<uint4*>(P.o_lo + off) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         if (!live) continue;
         if (P.out_mode == 0) {
 #pragma unroll

@@ -308,6 +308,8 @@ struct Gn2Args {
   uint8_t* o_hi; uint8_t* o_lo; int64_t o_plane; int o_chunk0;
   const float* p_w; const float* p_b; float* eps;
   int x3;                                                    // 0: single-pass mode, the convs read only the hi plane: no lo work
+  const float* cx; const float* cw; const float* cb;         // in == null: the input is the network's first conv (Cin = 1, k = 5) of cx (n, L), computed here
+  int zero_pads;                                             // out_mode 0: also write the two zero rows after the sample
 };
 
 // GroupNorm(8) + Mish (+ FiLM) (+ residual) for one sample per CTA, one warp per group.  A lane item is 8 channels
@@ -330,8 +332,24 @@ __global__ void __launch_bounds__(256) gn2_kernel(Gn2Args a) {
       const int c = j / a.L, l = j - c * a.L;
       const int chunk = grp * cq + c;
       const int64_t row = b * a.L + l;
-      const float4 v0 = *reinterpret_cast<const float4*>(a.in + ((int64_t)(2 * chunk) * a.in_rows + row) * 4);
-      const float4 v1 = *reinterpret_cast<const float4*>(a.in + ((int64_t)(2 * chunk + 1) * a.in_rows + row) * 4);
+      float4 v0, v1;
+      if (a.in) {
+        v0 = *reinterpret_cast<const float4*>(a.in + ((int64_t)(2 * chunk) * a.in_rows + row) * 4);
+        v1 = *reinterpret_cast<const float4*>(a.in + ((int64_t)(2 * chunk + 1) * a.in_rows + row) * 4);
+      } else {   // diffusion_utils.py:80-97 with Cin = 1: 5 MACs per output
+        float xv[5], o[8];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) { const int ll = l + t - 2; xv[t] = (ll >= 0 && ll < a.L) ? a.cx[row + t - 2] : 0.f; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int co = chunk * 8 + e;
+          float sacc = a.cb[co];
+#pragma unroll
+          for (int t = 0; t < 5; ++t) sacc = fmaf(a.cw[co * 5 + t], xv[t], sacc);
+          o[e] = sacc;
+        }
+        v0 = make_float4(o[0], o[1], o[2], o[3]); v1 = make_float4(o[4], o[5], o[6], o[7]);
+      }
       x[k][0] = v0.x; x[k][1] = v0.y; x[k][2] = v0.z; x[k][3] = v0.w;
       x[k][4] = v1.x; x[k][5] = v1.y; x[k][6] = v1.z; x[k][7] = v1.w;
       s += ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
@@ -421,6 +439,12 @@ __global__ void __launch_bounds__(256) gn2_kernel(Gn2Args a) {
       if (a.x3) *reinterpret_cast<uint4*>(a.o_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
+  if (a.zero_pads && a.out_mode == 0 && (int)threadIdx.x < (a.C / 8) * 2) {
+    const int chunk = threadIdx.x >> 1, l = a.L + (threadIdx.x & 1);
+    const int64_t off = (int64_t)(a.o_chunk0 + chunk) * a.o_plane + (4 + b * Lp + l) * 16;
+    *reinterpret_cast<uint4*>(a.o_hi + off) = make_uint4(0u, 0u, 0u, 0u);
+    if (a.x3) *reinterpret_cast<uint4*>(a.o_lo + off) = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (a.out_mode == 2) {      // final_conv.1 (Conv1d(128,1,1)): fixed-order sum over groups and chunks -> deterministic
     __syncthreads();
     const int l = threadIdx.x;
@@ -451,13 +475,14 @@ int launch_gn2(const Gn2Args& a, cudaStream_t s) {
 struct ZeroPadArgs {
   struct Buf { uint8_t* base; int64_t plane; int nplanes, L; } buf[7];
   int64_t n;
+  int edges_only;     // the fused convs write the rows after each sample themselves: only rows 0..3 and the tail are left
 };
 __global__ void __launch_bounds__(256) zero_pads_kernel(const __grid_constant__ ZeroPadArgs a) {
   const ZeroPadArgs::Buf& B = a.buf[blockIdx.y];
-  const int64_t per = a.n + 1;
+  const int64_t per = a.edges_only ? 1 : a.n + 1;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= per * B.nplanes) return;
-  const int64_t pl = idx / per, j = idx - pl * per;
+  const int64_t pl = idx / per, j = a.edges_only ? a.n : idx - pl * per;
   uint4* p = reinterpret_cast<uint4*>(B.base + pl * B.plane);
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   const int Lp = B.L + 2;
@@ -530,14 +555,16 @@ int res_block_tc(const TcRun& R, const TcBufs& B, int bi, const ActBuf& in, int 
     P.out_mode = 2; P.res_mode = 0; P.o_split = 0; P.o_hi = h.hi; P.o_lo = h.lo; P.o_plane = h.plane; P.o_chunk0 = 0;
     DGDM_TRY(conv_gn(R, P, in, in_chunk0, ci, R.pl.conv0[bi], w.conv0_b, w.gn0_w, w.gn0_b, B.film[bi], co, L));
   } else {
-    if (ci == 1) {
+    Gn2Args g0{};
+    if (ci == 1 && fused) {
+      g0.cx = x_in; g0.cw = w.conv0_w; g0.cb = w.conv0_b; g0.zero_pads = 1;
+    } else if (ci == 1) {
       conv_in_kernel<<<nblk(R.n * L * (co / 4), 256), 256, 0, R.s>>>(B.t0, x_in, w.conv0_w, w.conv0_b, R.n, L, co);
       DGDM_LAUNCH_CHECK();
     } else {
       DGDM_TRY(conv_to_f32(R, in, in_chunk0, ci, 5, 0, R.pl.conv0[bi], w.conv0_b, co, L, B.t0));
     }
-    Gn2Args g0{};
-    g0.in = B.t0; g0.in_rows = R.n * L; g0.gamma = w.gn0_w; g0.beta = w.gn0_b; g0.film = B.film[bi]; g0.n = R.n; g0.L = L; g0.C = co;
+    g0.in = g0.cx ? nullptr : B.t0; g0.in_rows = R.n * L; g0.gamma = w.gn0_w; g0.beta = w.gn0_b; g0.film = B.film[bi]; g0.n = R.n; g0.L = L; g0.C = co;
     g0.x3 = R.x3; g0.res_mode = 0; g0.out_mode = 0; g0.o_hi = h.hi; g0.o_lo = h.lo; g0.o_plane = h.plane; g0.o_chunk0 = 0;
     DGDM_TRY(launch_gn2(g0, R.s));
   }
@@ -604,9 +631,9 @@ int unet_forward_tc(const dgdm_unet_weights* w, const float* x, int64_t n, int P
     int64_t most = 0;
     for (int i = 0; i < 7; ++i) {   // hi planes, then (fp32-grade mode only: the single-pass convs never read them) lo planes
       za.buf[i] = {bufs[i]->hi, bufs[i]->plane, R.x3 ? 2 * chunks[i] : chunks[i], i < 2 ? L : L2};
-      most = std::max<int64_t>(most, (int64_t)za.buf[i].nplanes * (nc + 1));
+      most = std::max<int64_t>(most, (int64_t)za.buf[i].nplanes * (gn_fused(R, L) ? 1 : nc + 1));
     }
-    za.n = nc;
+    za.n = nc; za.edges_only = gn_fused(R, L);
     zero_pads_kernel<<<dim3((unsigned)nblk(most, 256), 7), 256, 0, s>>>(za);
     DGDM_LAUNCH_CHECK();
   }

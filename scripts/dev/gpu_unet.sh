@@ -7,12 +7,12 @@ for f in 0 1; do
     echo -n "fused=$f  "; DGDM_UNET_FUSED=$f python scripts/dev/unet_time.py $cfg 2>&1 | tail -1
   done
 done
+if [ "$1" = "prof" ]; then
 for cfg in "bf16 14 16384" "fp32 42 8192"; do set -- $cfg
-  ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_uniform.sum,sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -s 60 -c 30 --csv \
+  ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -s 54 -c 27 --csv \
       --log-file gpurun_out/unet_launches_r02_$1_p$2.csv python scripts/dev/unet_time.py $cfg > /dev/null 2>&1; echo "launch list $cfg rc=$?"
 done
-ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 66 -c 4 -f -o gpurun_out/conv_gn_r02_bf16_p14 \
-      python scripts/dev/unet_time.py bf16 14 16384 > /dev/null 2>&1; echo "ncu rc=$?"
+fi
 python bench.py --workload c3 --precision bf16 --steps 5 --warmup 3 --no-extra 2>&1 | tail -1 | python -c "
 import sys, json; d = json.loads(sys.stdin.read()); print('c3 bf16', d['value'], d['roofline']['frac'], d['ms_per_step'])"
 python bench.py --steps 5 --warmup 3 --no-extra 2>&1 | tail -1 | python -c "
