@@ -206,6 +206,42 @@ def test_unet_batch_position_independence(P, g2, precision):
     assert torch.equal(got, ref[idx])
 
 
+_UNET_VARIANT_SCRIPT = r"""
+import sys
+sys.path[:0] = [sys.argv[1], sys.argv[1] + "/tests", sys.argv[1] + "/oracle"]
+import torch
+from dgdm_b200 import synthetic as syn
+from dgdm_b200.diffusion import Diffusion
+from dgdm_b200.scheduler import DDIMScheduler
+out = {}
+for prec in ("fp32", "bf16"):
+    for P, n in ((14, 300), (42, 130), (8, 65)):
+        dm = Diffusion(syn.unet1d_state_dict(0), DDIMScheduler(15), 5, mode="point", num_points=P, class_cond=False, precision=prec)
+        out[f"{prec}_{P}"] = dm.noise_pred_net(syn.initial_noise(n, P, seed=5).cuda(), 9).cpu()
+torch.save(out, sys.argv[2])
+"""
+
+
+def test_unet_fused_and_two_launch_forms_agree(tmp_path):
+    """The denoiser's Conv1dBlocks run as one launch each (GroupNorm in the conv epilogue); DGDM_UNET_FUSED=0 keeps the
+    round-1 form (conv -> fp32 -> gn2_kernel).  Same operands and the same two-pass statistics, different summation
+    trees: they must agree to fp32 rounding in the fp32-grade mode and to operand precision in bf16."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, env in (("fused", {}), ("two_launch", {"DGDM_UNET_FUSED": "0"})):
+        path = str(tmp_path / f"unet_{name}.pt")
+        r = subprocess.run([sys.executable, "-c", _UNET_VARIANT_SCRIPT, repo, path], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, (name, r.stderr[-3000:])
+        res[name] = torch.load(path)
+    for k, a in res["fused"].items():
+        tol = 2e-5 if k.startswith("fp32") else 1e-2
+        assert rel(a, res["two_launch"][k]) < tol, (k, rel(a, res["two_launch"][k]))
+
+
 # ---------------------------------------------------------------------------------------------- K1+K2
 @pytest.mark.parametrize("precision", ALL_MODES)
 def test_cond_fn_2d_golden(g2, precision):
