@@ -72,6 +72,15 @@ __global__ void pose_embed_kernel(float* __restrict__ pose, dgdm_pose_grid grid,
 }
 
 // timestep_embedding(t, dim): [cos(t f_i), sin(t f_i)], f_i = exp(-ln(1e4) i / half)  (profile_forward_2d.py:58-76)
+// V [G][H1] -> Vq [H1/4][G][4]: the tensor-core trunk reads four layer-1 features of a pose row with one 128-bit load,
+// consecutive lanes = consecutive pose rows (512 contiguous bytes per warp request).
+__global__ void pose_table_quads_kernel(float4* __restrict__ vq, const float* __restrict__ V, int G, int H1) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * (H1 / 4)) return;
+  const int c4 = idx / G, g = idx - c4 * G;
+  vq[idx] = *reinterpret_cast<const float4*>(V + (size_t)g * H1 + 4 * c4);
+}
+
 __global__ void time_embed_kernel(float* __restrict__ out, float t, int dim) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int half = dim / 2;
@@ -293,8 +302,9 @@ int run_hoists(const dgdm_dyn_weights* w, const float* x, int nd, const float* o
   pose_embed_kernel<<<blocks_for(h.G, 128), 128, 0, s>>>(h.pose, *grid, h.G);
   DGDM_LAUNCH_CHECK();
   DGDM_TRY(gemm_f32(gemm_plain(h.pose, 27, w->w1_pose, nullptr, h.V, H1, h.G, H1, 27, ACT_NONE), s));
-  // the same table transposed ([H1][G]) for the tensor-core trunk's coalesced per-row reads
-  DGDM_TRY(gemm_f32(gemm_plain(w->w1_pose, 27, h.pose, nullptr, h.Vt, h.G, H1, h.G, 27, ACT_NONE), s));
+  // the same table as [H1/4][G][4] for the tensor-core trunk's coalesced 128-bit per-row reads
+  pose_table_quads_kernel<<<blocks_for((int64_t)h.G * (H1 / 4), 256), 256, 0, s>>>(reinterpret_cast<float4*>(h.Vt), h.V, h.G, H1);
+  DGDM_LAUNCH_CHECK();
   // time: 2D = MLP(SiLU) of a 128-d embedding; 3D = raw 256-d embedding (profile_forward_3d.py:83)
   const float* te;
   if (w->is_3d) {

@@ -94,7 +94,7 @@ struct Seg {
 
 struct TcParams {
   const uint8_t* img;
-  const float* U; const float* Cst; const float* Vt;   // Vt: pose table transposed, [H1][G]
+  const float* U; const float* Cst; const float* Vt;   // Vt: pose table in quads, [H1/4][G][4]
   const float* bias[7]; const float* w_out; const float* b_out;
   const int32_t* pair_object;
   float* part;          // [n_slots][H1] per-(pair,tile) partial column sums  (backward)
@@ -153,6 +153,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     }
   }
 }
+// (A suspend-time hint on try_wait -- 2 us / 20 us, so that a warp waiting for a layer of MMAs sleeps in one try_wait instead of
+// polling every ~200 cycles, 17 % of the bf16 trunk's executed instructions -- measured 1 % SLOWER on the same box: the wake-up is
+// later, and the polling warps were not taking issue slots anybody needed.)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -615,12 +618,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
       // The pose table is read TRANSPOSED ([H1][G]): lanes are consecutive pose rows g, so each feature is one
       // coalesced 128-byte request; all loads are issued before use.  U/Cst rows are warp-broadcast loads.
       auto load_z = [&](int col0, float (&z)[16]) {
-        float pv[16];
+        float4 pv[4];
         {
-          const float* vt = P.Vt + (int64_t)col0 * P.G + g;
-          const uint32_t G32 = (uint32_t)P.G;
+          // 32-bit byte offsets from the (uniform) table base: one add per load instead of a 64-bit multiply-add chain
+          // (the address arithmetic was half of this function's instructions, and the epilogue is issue-bound)
+          const char* vb = reinterpret_cast<const char*>(P.Vt);
+          const uint32_t step = (uint32_t)P.G * 16u;
+          uint32_t off = (uint32_t)(col0 >> 2) * step + (uint32_t)g * 16u;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pv[i] = live ? __ldg(vt + i * G32) : 0.f;
+          for (int i = 0; i < 4; ++i, off += step) pv[i] = live ? __ldg(reinterpret_cast<const float4*>(vb + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
@@ -628,7 +634,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           if (live) {
             float4 k4 = *reinterpret_cast<const float4*>(c_row + col0 + i);
             float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + i);
-            a.x = (k4.x + u4.x) + pv[i]; a.y = (k4.y + u4.y) + pv[i + 1]; a.z = (k4.z + u4.z) + pv[i + 2]; a.w = (k4.w + u4.w) + pv[i + 3];
+            const float4 p4 = pv[i >> 2];
+            a.x = (k4.x + u4.x) + p4.x; a.y = (k4.y + u4.y) + p4.y; a.z = (k4.z + u4.z) + p4.z; a.w = (k4.w + u4.w) + p4.w;
           }
           if (F16) { a.x *= F16_SA; a.y *= F16_SA; a.z *= F16_SA; a.w *= F16_SA; }     // fp16 modes: operands are a * SA
           z[i] = a.x; z[i + 1] = a.y; z[i + 2] = a.z; z[i + 3] = a.w;
@@ -710,11 +717,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
               S.mask[mbase + kb * 4 + hq][row] = (uint16_t)sign_bits16(hi);   // after the hand-off: off the critical path
             } else {
               const uint32_t bits = S.mask[mbase + kb * 4 + hq][row];
-              float v[16];
+              if constexpr (!X3) {
+                // single-pass modes: convert first, then clear the masked halfwords of each packed word -- shift the
+                // pair's two sign bits to the top of bytes 0 / 1, PRMT replicates them into a halfword mask, one AND:
+                // 3 instructions per two elements instead of 4 (test + select each); same bits as select-then-convert
+                uint32_t hi[8], lo[8];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = (bits >> mask_pos(i)) & 1u ? unscale<F16, X3>(rr[kb & 1][i]) : 0.f;
-              TRE(kb, 7);
-              store_a(dreg, kb, v);
+                for (int i = 0; i < 8; ++i) {
+                  const float v0 = unscale<F16, X3>(rr[kb & 1][2 * i]), v1 = unscale<F16, X3>(rr[kb & 1][2 * i + 1]);
+                  uint32_t w;
+                  if (F16) w = cvt_rn_f16x2(v0, v1);
+                  else { __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1); w = *reinterpret_cast<uint32_t*>(&h); }
+                  uint32_t m;
+                  asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(m) : "r"(bits << (7 - mask_pos(2 * i))));
+                  hi[i] = w & m;
+                }
+                TRE(kb, 7);
+                store_packed(dreg, kb, hi, lo);
+              } else {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = (bits >> mask_pos(i)) & 1u ? unscale<F16, X3>(rr[kb & 1][i]) : 0.f;
+                TRE(kb, 7);
+                store_a(dreg, kb, v);
+              }
               TRE(kb, 8);
               signal_kb(kb);
             }
@@ -887,9 +913,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk_kernel(const __grid_cons
           } else
           for (int64_t ps = p_first; ps <= p_last; ++ps) {
             const bool mine = pr == ps;
+            const bool any_mine = __any_sync(0xffffffffu, mine);   // a warp with no row of this pair contributes exact zeros
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
               const int cc = hq * 2 + c;
+              if (!any_mine) { S.red[q][cc * 32 + lane] = 0.f; continue; }
               uint32_t rr[32];
               tmem_ld32(d_addr + (uint32_t)(cc * 32), rr);
               const uint32_t b0 = mine ? S.mask[(sgm.half * 8 + cc) * 2][row] : 0u, b1 = mine ? S.mask[(sgm.half * 8 + cc) * 2 + 1][row] : 0u;
@@ -1195,18 +1223,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_trunk2_kernel(const __grid_con
             c_row = P.Cst + (int64_t)pair_obj(pr, P.opd, P.n_designs, P.n_obj, P.pair_object) * P.H1;
           }
           auto load_z = [&](int col0, float (&z)[16]) {
-            float pv[16];
-            const float* vt = P.Vt + (int64_t)col0 * P.G + g;
-            const uint32_t G32 = (uint32_t)P.G;
+            float4 pv[4];
+            const char* vb = reinterpret_cast<const char*>(P.Vt);
+            const uint32_t step = (uint32_t)P.G * 16u;
+            uint32_t off = (uint32_t)(col0 >> 2) * step + (uint32_t)g * 16u;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) pv[k] = live ? __ldg(vt + k * G32) : 0.f;
+            for (int k = 0; k < 4; ++k, off += step) pv[k] = live ? __ldg(reinterpret_cast<const float4*>(vb + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < 16; k += 4) {
               float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
               if (live) {
                 const float4 k4 = *reinterpret_cast<const float4*>(c_row + col0 + k);
                 const float4 u4 = *reinterpret_cast<const float4*>(u_row + col0 + k);
-                a.x = (k4.x + u4.x) + pv[k]; a.y = (k4.y + u4.y) + pv[k + 1]; a.z = (k4.z + u4.z) + pv[k + 2]; a.w = (k4.w + u4.w) + pv[k + 3];
+                const float4 p4 = pv[k >> 2];
+                a.x = (k4.x + u4.x) + p4.x; a.y = (k4.y + u4.y) + p4.y; a.z = (k4.z + u4.z) + p4.z; a.w = (k4.w + u4.w) + p4.w;
               }
               if (F16) { a.x *= F16_SA; a.y *= F16_SA; a.z *= F16_SA; a.w *= F16_SA; }
               z[k] = a.x; z[k + 1] = a.y; z[k + 2] = a.z; z[k + 3] = a.w;
@@ -1674,6 +1704,7 @@ int tc_trunk(const dgdm_dyn_weights* w, const float* U, const float* Cst, const 
   const bool x3_mode = precision == DGDM_PREC_BF16X3 || precision == DGDM_PREC_FP16X3;
   P.img = (const uint8_t*)w->tc_image + (f16 ? (x3_mode ? pl.bytes : 2 * pl.bytes) : 0);
   P.gscale = f16 ? F16_GS : 1.f;
+  DGDM_CHECK_ARG((int64_t)H1 * G * 4 < (1ll << 32), "tc_trunk: pose table of %d x %d exceeds 32-bit byte offsets", H1, G);
   P.U = U; P.Cst = Cst; P.Vt = V;
   for (int i = 0; i < 7; ++i) P.bias[i] = w->bl[i];
   P.w_out = w->w_out; P.b_out = w->b_out;
