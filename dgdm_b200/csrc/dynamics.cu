@@ -250,6 +250,7 @@ struct RowLinear {
 
 struct Hoist {
   float *h0, *e, *U, *Cst, *V, *Vt, *pose, *temb, *th, *te, *tc, *oh, *oc, *dUp, *dU, *de, *dh0, *score_sum;
+  uint8_t* lin_scratch; int* lin_err;     // packed-weight scratch + error word of the tcgen05 linear kernel (RowLinear)
   int G;
   int64_t n_pairs;
 };
@@ -265,6 +266,7 @@ size_t hoist_bytes(int P, int H1, int obj_dim, int64_t nd, int n_obj, int64_t n_
   b += a((size_t)n_obj * 256) * 2;                       // oh, oc
   b += a(n_pairs * H1) + a(nd * H1) + a(nd * 256) * 2;   // dUp, dU, de, dh0
   b += a(n_pairs);                                       // score_sum
+  b += align_up(RowLinear::ROW_SCRATCH_BYTES, 256) + 256; // lin_scratch, lin_err
   (void)P; (void)obj_dim;
   return b;
 }
@@ -292,12 +294,17 @@ int check_common(const dgdm_dyn_weights* w, const float* x, int n_designs, const
 
 // Everything that does not scale with B*G.
 int run_hoists(const dgdm_dyn_weights* w, const float* x, int nd, const float* objects, int n_obj, float t_frac,
-               const dgdm_pose_grid* grid, Hoist& h, cudaStream_t s) {
+               const dgdm_pose_grid* grid, Hoist& h, int precision, cudaStream_t s) {
   const int H1 = w->H1, P = w->P;
+  // The design-sized GEMMs (K, N multiples of 64 / 256) run on the tcgen05 linear kernel in fp32-grade arithmetic in
+  // every tensor-core mode (they were 1-2 % of a pass on CUDA cores); fp32_simt keeps exact fp32 throughout.
+  const bool tc = precision != DGDM_PREC_FP32_SIMT;
+  if (tc) DGDM_CUDA(cudaMemsetAsync(h.lin_err, 0, sizeof(int), s));
+  const RowLinear lin{tc, h.lin_scratch, h.lin_err, s};
   // gripper encoder: 14|42 -> 256 -> 256 (ReLU between), then its layer-1 block
   DGDM_TRY(gemm_f32(gemm_plain(x, P, w->ge_w0, w->ge_b0, h.h0, 256, nd, 256, P, ACT_RELU), s));
-  DGDM_TRY(gemm_f32(gemm_plain(h.h0, 256, w->ge_w1, w->ge_b1, h.e, 256, nd, 256, 256, ACT_NONE), s));
-  DGDM_TRY(gemm_f32(gemm_plain(h.e, 256, w->w1_ctrl, nullptr, h.U, H1, nd, H1, 256, ACT_NONE), s));
+  DGDM_TRY(lin(gemm_plain(h.h0, 256, w->ge_w1, w->ge_b1, h.e, 256, nd, 256, 256, ACT_NONE)));
+  DGDM_TRY(lin(gemm_plain(h.e, 256, w->w1_ctrl, nullptr, h.U, H1, nd, H1, 256, ACT_NONE)));
   // pose table
   pose_embed_kernel<<<blocks_for(h.G, 128), 128, 0, s>>>(h.pose, *grid, h.G);
   DGDM_LAUNCH_CHECK();
@@ -354,6 +361,8 @@ int carve(const dgdm_dyn_weights* w, int nd, int n_obj, int opd, const dgdm_pose
   h.de = ar.take<float>((size_t)nd * 256);
   h.dh0 = ar.take<float>((size_t)nd * 256);
   h.score_sum = ar.take<float>((size_t)h.n_pairs);
+  h.lin_scratch = ar.take<uint8_t>(RowLinear::ROW_SCRATCH_BYTES);
+  h.lin_err = ar.take<int>(1);
   return DGDM_OK;
 }
 
@@ -555,16 +564,17 @@ extern "C" int dgdm_dyn_guidance(const dgdm_dyn_weights* w, const float* x, int3
   Hoist h{};
   carve(w, n_designs, n_obj, objs_per_design, grid, ar, h);
   if (!ar.ok) { set_error("dgdm_dyn_guidance: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
-  DGDM_TRY(run_hoists(w, x, n_designs, objects, n_obj, t_frac, grid, h, s));
+  DGDM_TRY(run_hoists(w, x, n_designs, objects, n_obj, t_frac, grid, h, precision, s));
   DGDM_TRY(trunk_dispatch(w, h, n_designs, n_obj, objs_per_design, pair_object, objective, true, logits, ar, precision, s));
   const int H1 = w->H1, P = w->P;
   // K2 tail: fold pairs into designs, then the gripper-encoder backward (B-sized GEMMs)
   fold_pairs_kernel<<<blocks_for((int64_t)n_designs * H1, 256), 256, 0, s>>>(h.dU, h.dUp, n_designs, H1, objs_per_design, grad_mul);
   DGDM_LAUNCH_CHECK();
-  DGDM_TRY(gemm_f32(gemm_plain(h.dU, H1, w->w1_ctrl_t, nullptr, h.de, 256, n_designs, 256, H1, ACT_NONE), s));
+  const RowLinear lin{precision != DGDM_PREC_FP32_SIMT, h.lin_scratch, h.lin_err, s};
+  DGDM_TRY(lin(gemm_plain(h.dU, H1, w->w1_ctrl_t, nullptr, h.de, 256, n_designs, 256, H1, ACT_NONE)));
   GemmArgs g = gemm_plain(h.de, 256, w->ge_w1_t, nullptr, h.dh0, 256, n_designs, 256, 256, ACT_NONE);
   g.mask = h.h0;
-  DGDM_TRY(gemm_f32(g, s));
+  DGDM_TRY(lin(g));
   DGDM_TRY(gemm_f32(gemm_plain(h.dh0, 256, w->ge_w0_t, nullptr, grad, P, n_designs, P, 256, ACT_NONE), s));
   return DGDM_OK;
 }
@@ -582,7 +592,7 @@ extern "C" int dgdm_dyn_score(const dgdm_dyn_weights* w, const float* x, int32_t
   Hoist h{};
   carve(w, n_designs, n_obj, objs_per_design, grid, ar, h);
   if (!ar.ok) { set_error("dgdm_dyn_score: workspace too small (need >= %zu bytes)", ar.off); return DGDM_EWORKSPACE; }
-  DGDM_TRY(run_hoists(w, x, n_designs, objects, n_obj, t_frac, grid, h, s));
+  DGDM_TRY(run_hoists(w, x, n_designs, objects, n_obj, t_frac, grid, h, precision, s));
   DGDM_TRY(trunk_dispatch(w, h, n_designs, n_obj, objs_per_design, pair_object, objective, false, logits, ar, precision, s));
   scale_kernel<<<blocks_for(h.n_pairs, 256), 256, 0, s>>>(scores, h.score_sum, h.n_pairs, 1.f / (float)h.G);
   DGDM_LAUNCH_CHECK();
