@@ -163,6 +163,7 @@ def test_linear_tc(M, N, K, precision):
 
 
 # ---------------------------------------------------------------------------------------------- K3
+CONV_SINGLE_PASS_TOL = 0.35    # 2x the worst measured on the 2D golden fixture (bf16 0.17 / 0.11, fp16 0.072 / 0.074)
 UNET_TOL = {"fp32_simt": 1e-4, "fp32": 1e-3, "bf16": 2e-2, "fp16": 1e-3}   # fp16 is a trunk mode: its denoiser is fp32-grade
 
 
@@ -290,8 +291,15 @@ def test_convergence_2d_golden(g2, precision):
         c = dm.get_convergence_centers(ung, dm.object_vertices[oi], 4)
         assert c.tolist() == g2[f"conv_centers_o{oi}"].tolist()
         got = dm.cond_fn(noise, 9, opt_obj="convergence", object_vertices=dm.object_vertices[oi], convergence_centers=c)
-        if precision not in ("bf16", "fp16"):    # +/- cancellation over 24 rows leaves bf16 nothing to average; fp32 modes only
-            grad_close(got, g2[f"grad_o{oi}_t9_convergence"], TOL[precision])
+        want = g2[f"grad_o{oi}_t9_convergence"]
+        if precision not in ("bf16", "fp16"):
+            grad_close(got, want, TOL[precision])
+        else:
+            # single-pass modes: the +/- cancellation of this objective over 24 pose rows leaves operand rounding nothing to
+            # average over, so only a loose bound holds -- but a wrong sign, scale or row mapping would still break it
+            err = rel(got, want)
+            print(f"[convergence {precision} o{oi}] rel-err {err:.3e}")
+            assert err < CONV_SINGLE_PASS_TOL, err
 
 
 @pytest.mark.parametrize("precision", ALL_MODES)
